@@ -1,0 +1,206 @@
+"""
+Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+    python oracle/make_golden.py [--only NAME] [--big]
+
+Every fixture stores the seeds/config needed to regenerate its inputs (weights come from
+orca_b200.synthetic.fill_state_dict, inputs from numpy PCG64) and the reference outputs.
+The script also asserts that oracle/orca_oracle.py reproduces each output (<= 2e-6 of max),
+which is what pins the oracle.
+"""
+import argparse
+import os
+import sys
+import time
+import types
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+warnings.filterwarnings("ignore")
+
+
+def import_reference():
+    """Import orca_modules / orca_models / orca_predict from the read-only reference tree,
+    stubbing the data-access dependencies that are not installed."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name, attrs in {
+        "selene_utils2": ["MemmapGenome", "Genomic2DFeatures"],
+        "selene_sdk": [],
+        "selene_sdk.sequences": ["Genome"],
+        "orca_utils": ["genomeplot", "genomeplot_256Mb", "StructuralChange2", "process_anno", "coord_round", "coord_clip"],
+    }.items():
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            for a in attrs:
+                setattr(mod, a, type(a, (), {}))
+            sys.modules[name] = mod
+    sys.modules["selene_sdk"].sequences = sys.modules["selene_sdk.sequences"]
+    import orca_modules
+    import orca_predict
+    return orca_modules, orca_predict
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def randn(shape, seed, scale=1.0):
+    return torch.from_numpy((np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32))
+
+
+def save(name, **arrays):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("  wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--big", action="store_true", help="also run the 32 Mb genomepredict golden (minutes)")
+    args = ap.parse_args()
+    om, op = import_reference()
+    import orca_oracle as oracle
+    from orca_b200 import synthetic, models
+
+    torch.set_num_threads(os.cpu_count())
+
+    def want(name):
+        return args.only is None or args.only == name
+
+    def ref_module(cls, seed, *a, **k):
+        return synthetic.init_module(cls(*a, **k), seed)
+
+    with torch.no_grad():
+        # ---------------- Encoder ----------------
+        for name, L, seed_x, nfrac in [("encoder_24k", 24000, 101, 0.02), ("encoder_1mb", 1000000, 102, 0.0)]:
+            if not want(name):
+                continue
+            t0 = time.time()
+            m = ref_module(om.Encoder, 11)
+            x = torch.from_numpy(synthetic.random_sequence(1, L, seed_x, nfrac)).transpose(1, 2)
+            y = m(x).numpy()
+            yo = oracle.encoder_forward(m.state_dict(), x).numpy()
+            print(name, y.shape, "oracle relerr %.2e" % relerr(yo, y), "absmax %.3f" % np.abs(y).max(), "%.1fs" % (time.time() - t0))
+            assert relerr(yo, y) < 2e-6
+            save(name, weight_seed=11, L=L, seq_seed=seed_x, n_fraction=nfrac, out=y)
+
+        # ---------------- Encoder2 / 2b / 3 ----------------
+        for name, cls, seed, P, n, up in [("encoder2_p256", om.Encoder2, 12, 256, 5, True),
+                                          ("encoder3_p64", om.Encoder3, 13, 64, 3, True),
+                                          ("encoder2b_p64", om.Encoder2b, 14, 64, 5, False)]:
+            if not want(name):
+                continue
+            m = ref_module(cls, seed)
+            x = randn((2, 128, P), 200 + seed)
+            ys = [t.numpy() for t in m(x)]
+            yo = [t.numpy() for t in oracle.encoder2_forward(m.state_dict(), x, n=n, up=up)]
+            errs = [relerr(a, b) for a, b in zip(yo, ys)]
+            print(name, [t.shape for t in ys], "oracle relerr", ["%.1e" % e for e in errs])
+            assert max(errs) < 2e-6 and len(yo) == len(ys)
+            save(name, weight_seed=seed, P=P, x_seed=200 + seed, **{"out%d" % i: t for i, t in enumerate(ys)})
+
+        # ---------------- Decoder ----------------
+        mats, _ = synthetic.normmats_32mb()
+        for name, mode, S, B, coarse, level in [("decoder_nocoarse_250", "bilinear", 250, 1, False, 32),
+                                                ("decoder_coarse_bilinear_250", "bilinear", 250, 1, True, 4),
+                                                ("decoder_coarse_nearest_64", "nearest", 64, 2, True, 1),
+                                                ("decoder_nocoarse_nearest_30", "nearest", 30, 2, False, 1)]:
+            if not want(name):
+                continue
+            t0 = time.time()
+            m = ref_module(om.Decoder, 15, upsample_mode=mode)
+            x = randn((B, 128, S), 301, 0.5)
+            distenc = torch.log(torch.FloatTensor(mats[level][:S, :S][None, None])).expand(B, -1, -1, -1)
+            yc = randn((B, 1, S // 2, S // 2), 302) if coarse else None
+            y = m(x, distenc, yc).numpy()
+            yo = oracle.decoder_forward(m.state_dict(), x, distenc, yc, mode).numpy()
+            print(name, y.shape, "oracle relerr %.2e" % relerr(yo, y), "absmax %.3f" % np.abs(y).max(), "%.1fs" % (time.time() - t0))
+            assert relerr(yo, y) < 2e-6
+            save(name, weight_seed=15, mode=mode, S=S, B=B, coarse=coarse, level=level, x_seed=301, y_seed=302, out=y)
+
+        for name, S, B in [("decoder1m_250", 250, 1), ("decoder1m_40", 40, 2)]:
+            if not want(name):
+                continue
+            m = ref_module(om.Decoder_1m, 16)
+            x = randn((B, 128, S), 303, 0.5)
+            y = m(x).numpy()
+            yo = oracle.decoder_1m_forward(m.state_dict(), x).numpy()
+            print(name, y.shape, "oracle relerr %.2e" % relerr(yo, y), "absmax %.3f" % np.abs(y).max())
+            assert relerr(yo, y) < 2e-6
+            save(name, weight_seed=16, S=S, B=B, x_seed=303, out=y)
+
+        # ---------------- Net ----------------
+        if want("net_48k"):
+            m = ref_module(om.Net, 17, num_1d=32)
+            x = torch.from_numpy(synthetic.random_sequence(2, 48000, 104, 0.01)).transpose(1, 2)
+            pred, p1d = m(x)
+            po, p1o = oracle.net_forward(m.state_dict(), x, num_1d=32)
+            print("net_48k", pred.shape, p1d.shape, "oracle relerr %.2e %.2e" % (relerr(po.numpy(), pred.numpy()), relerr(p1o.numpy(), p1d.numpy())))
+            assert relerr(po.numpy(), pred.numpy()) < 2e-6 and relerr(p1o.numpy(), p1d.numpy()) < 2e-6
+            save("net_48k", weight_seed=17, L=48000, B=2, seq_seed=104, n_fraction=0.01, num_1d=32, out=pred.numpy(), out_1d=p1d.numpy())
+
+        # ---------------- background levels (orca_predict.py:724-737, :693-703) ----------------
+        if want("background"):
+            nm = synthetic.normmat_256mb(chrlen_bins=6000)
+            outs = {}
+            for tag, r0, level, flip in [("l256", 0, 256, False), ("l64_r", 1500, 64, True), ("l32", 4100, 32, False)]:
+                f = level // 8
+                r = np.nanmean(np.nanmean(np.reshape(nm[r0:r0 + 250 * f, r0:r0 + 250 * f], (1, 250, f, 250, f)), axis=4), axis=2)
+                d = torch.log(torch.FloatTensor(r[None, :, :]))
+                if flip:
+                    d = torch.flip(d, [2, 3])
+                do = oracle.background_level(nm, r0, f, 250, flip)
+                assert relerr(do.numpy(), d.numpy()) < 1e-7
+                outs[tag] = d.numpy()
+            print("background ok")
+            save("background", chrlen_bins=6000, **outs)
+
+        # ---------------- genomepredict through the unmodified driver ----------------
+        if want("genomepredict_32mb") and args.big:
+            t0 = time.time()
+            shell = models.build_shell(om, "h1esc", seed=7)
+            seq = synthetic.random_sequence(1, 32000000, 105)
+            mpos, wpos = 16500000, 16000000
+            res = op.genomepredict(seq, "chrS", mpos, wpos, models=[shell], use_cuda=False)
+            preds = np.stack(res["predictions"][0]).astype(np.float32)
+            print("genomepredict_32mb", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
+            save("genomepredict_32mb", shell_seed=7, seq_seed=105, mpos=mpos, wpos=wpos, predictions=preds,
+                 start_coords=np.asarray(res["start_coords"], dtype=np.int64))
+
+        if want("genomepredict_256mb_stub"):
+            # Driver logic of genomepredict_256Mb with a stub net0 (a seeded random 4 kb encoding), so the
+            # fixture exercises net1(...)[-1], Encoder3, the background levels and the cascade index math
+            # without the 10-minute CPU encoder.
+            t0 = time.time()
+            shell = models.build_shell(om, "h1esc_256m", seed=8)
+
+            class StubNet0(torch.nn.Module):
+                def forward(self, x):
+                    g = np.random.default_rng(106)  # same encoding on both strands: only the driver logic matters
+                    return torch.from_numpy((g.standard_normal((x.shape[0], 128, 64000)) * 0.5).astype(np.float32))
+            shell.net0 = StubNet0()
+            seq = synthetic.random_sequence(1, 4000, 107)
+            nm = synthetic.normmat_256mb(chrlen_bins=6000)
+            mpos, wpos, chrlen = 100000000, 128000000, 6000 * 32000
+            res = op.genomepredict_256Mb(seq, "chrS", [nm.copy()], chrlen, mpos, wpos, models=[shell], use_cuda=False)
+            preds = np.stack(res["predictions"][0]).astype(np.float32)
+            print("genomepredict_256mb_stub", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
+            save("genomepredict_256mb_stub", shell_seed=8, enc_seed=106, chrlen_bins=6000, mpos=mpos, wpos=wpos,
+                 chrlen=chrlen, predictions=preds, start_coords=np.asarray(res["start_coords"], dtype=np.int64))
+
+
+if __name__ == "__main__":
+    main()

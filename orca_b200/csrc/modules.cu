@@ -1,0 +1,773 @@
+// Host side of liborca_b200: module handles (BN folding + weight packing), the layer programs
+// of Encoder / Encoder2 / Encoder2b / Encoder3 / Decoder / Decoder_1m / Net, and the C ABI.
+// Layer programs follow /root/reference/orca_modules.py (cited per function); the arithmetic
+// itself lives in conv_simt.cu / conv_tc.cu / glue.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace orca {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_impl{ORCA_B200_IMPL_AUTO};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// architecture tables (what orca_b200_module_create validates against)
+// ---------------------------------------------------------------------------------------------
+struct Spec { int c_in, c_out, kh, kw, dil; };
+
+static void spec_encoder(std::vector<Spec>& v) {  // orca_modules.py:811-927
+  const int pool_cin[7] = {4, 64, 96, 128, 128, 128, 128};
+  const int cout[7] = {64, 96, 128, 128, 128, 128, 128};
+  for (int k = 0; k < 7; ++k) {
+    v.push_back({pool_cin[k], cout[k], 1, 9, 1});
+    for (int i = 0; i < 3; ++i) v.push_back({cout[k], cout[k], 1, 9, 1});
+  }
+}
+static void spec_unet(std::vector<Spec>& v, int n, bool up) {  // :991-1149, :1181-1264, :1286-1386
+  for (int i = 0; i < (up ? 8 : 4) * n; ++i) v.push_back({128, 128, 1, 9, 1});
+}
+static const int kDecDil[28] = {1, 2, 4, 8, 16, 32, 64, 1, 2, 4, 8, 16, 32, 64,
+                                1, 2, 4, 8, 16, 32, 64, 1, 2, 4, 8, 16, 32, 64};
+static const int kDec1mDil[19] = {1, 2, 4, 8, 16, 32, 64, 2, 4, 8, 16, 32, 64, 2, 4, 8, 16, 32, 64};
+
+static void spec_pairs(std::vector<Spec>& v, const int* dil, int n, int first_cin) {
+  for (int i = 0; i < n; ++i) {
+    v.push_back({i == 0 ? first_cin : 64, 32, 3, 3, dil[i]});
+    v.push_back({32, 64, 3, 3, dil[i]});
+  }
+}
+static void spec_final(std::vector<Spec>& v) {
+  v.push_back({64, 5, 1, 1, 1});
+  v.push_back({5, 1, 1, 1, 1});
+}
+static void spec_decoder(std::vector<Spec>& v) {  // orca_modules.py:22-459
+  spec_pairs(v, kDecDil, 28, 64);                 // lconvtwos
+  spec_pairs(v, kDecDil, 28, 64);                 // convtwos
+  spec_final(v);                                  // final
+  v.push_back({65, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // lcombiner
+  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // combiner
+  v.push_back({129, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});  // lcombinerD
+  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // combinerD
+}
+static void spec_decoder_1m(std::vector<Spec>& v) {  // orca_modules.py:499-780
+  spec_pairs(v, kDec1mDil, 19, 128);
+  spec_pairs(v, kDec1mDil, 19, 64);
+  spec_final(v);
+}
+
+// index helpers into module->L
+enum : int {
+  DEC_LCONV = 0, DEC_CONV = 56, DEC_FINAL = 112, DEC_LCOMB = 114, DEC_COMB = 116, DEC_LCOMBD = 118,
+  DEC_COMBD = 120, DEC_N = 122,
+  D1M_LCONV = 0, D1M_CONV = 38, D1M_FINAL = 76, D1M_N = 78,
+  ENC_N = 28
+};
+
+}  // namespace orca
+
+using namespace orca;
+
+struct orca_b200_module {
+  int kind = 0;
+  uint32_t flags = 0;
+  int num_1d = 0;
+  int device = 0;
+  std::vector<ConvLayer> L;
+  std::vector<void*> allocs;
+};
+
+namespace orca {
+
+// conv_tc.cu (optional tensor-core packing / dispatch)
+int tc_pack_layer(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
+bool tc_supported(const ConvLayer& L, const ConvCall& c);
+int conv_tc(const ConvLayer& L, const ConvCall& c, cudaStream_t s);
+
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launch stream ----
+struct ProfRec { cudaEvent_t e0, e1; int c_in, c_out, taps, dil, tc; double flop; };
+static std::atomic<int> g_profile{0};
+static std::vector<ProfRec> g_prof;  // single-threaded use (bench)
+
+static int conv_dispatch(const ConvLayer& L, const ConvCall& c, cudaStream_t s, bool* used_tc);
+
+static int conv(const ConvLayer& L, const ConvCall& c, cudaStream_t s) {
+  bool tc = false;
+  if (!g_profile.load(std::memory_order_relaxed)) return conv_dispatch(L, c, s, &tc);
+  ProfRec r;
+  ORCA_CUDA_OK(cudaEventCreate(&r.e0));
+  ORCA_CUDA_OK(cudaEventCreate(&r.e1));
+  ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
+  const int st = conv_dispatch(L, c, s, &tc);
+  ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
+  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = L.kh * L.kw; r.dil = L.dil; r.tc = tc ? 1 : 0;
+  r.flop = 2.0 * (double)c.B * c.H * c.W * L.c_in * L.c_out * L.kh * L.kw;
+  g_prof.push_back(r);
+  return st;
+}
+
+static int conv_dispatch(const ConvLayer& L, const ConvCall& c, cudaStream_t s, bool* used_tc) {
+  const int impl = g_impl.load(std::memory_order_relaxed);
+  *used_tc = false;
+  if (impl != ORCA_B200_IMPL_SIMT && tc_supported(L, c)) { *used_tc = true; return conv_tc(L, c, s); }
+  if (impl == ORCA_B200_IMPL_TC) {
+    set_error("ORCA_B200_IMPL_TC requested but the layer (%d->%d, %dx%d, d=%d) has no tcgen05 path", L.c_in,
+              L.c_out, L.kh, L.kw, L.dil);
+    return ORCA_B200_EUNSUPPORTED;
+  }
+  return conv_simt(L, c, s);
+}
+
+// ---- bump allocator over the caller's workspace (dry mode only measures) -----------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  bool failed = false;
+  float* f32(size_t n) { return reinterpret_cast<float*>(raw(n * sizeof(float))); }
+  void* raw(size_t bytes) {
+    const size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (dry) return reinterpret_cast<void*>(size_t(256));  // never dereferenced
+    if (off > cap) { failed = true; return nullptr; }
+    return base + a;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+#define ARENA_OK(ar)                                                                   \
+  do {                                                                                 \
+    if ((ar).failed) {                                                                 \
+      set_error("workspace too small (%zu bytes given, more needed)", (ar).cap);       \
+      return ORCA_B200_EWORKSPACE;                                                     \
+    }                                                                                  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Encoder body on one window:  x window -> out7 [nb][n/4000][128]
+// orca_modules.py:935-950 (run): 7 x { lout = BN(Conv(BN(Conv(pool(in))))) ;
+//   out = ReLU(BN(Conv(ReLU(BN(Conv(lout)))))) ; next in = out + lout } ; result = out7 (no residual)
+// ---------------------------------------------------------------------------------------------
+static const int kPool[7] = {1, 4, 4, 5, 5, 5, 2};
+
+static int encoder_window(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
+                          int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
+  const size_t m = ar.mark();
+  const size_t big = (size_t)nb * n * 64;
+  float* X0 = ar.f32(big);
+  float* X1 = ar.f32(big);
+  float* X2 = ar.f32(big);
+  float* Pb = ar.f32(big / 4);
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    int64_t len = n;
+    for (int k = 0; k < 7; ++k) {
+      const ConvLayer* Lk = L + 4 * k;
+      const int C = Lk[0].c_out;
+      ConvCall c;
+      c.B = nb; c.H = 1;
+      if (k == 0) {
+        ORCA_TRY(conv_first_simt(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, X0, s));
+      } else {
+        len /= kPool[k];
+        c.W = (int)len; c.in = Pb; c.in_ld = Lk[0].c_in; c.out = X0; c.out_ld = C;
+        ORCA_TRY(conv(Lk[0], c, s));
+      }
+      c.W = (int)len; c.in_ld = C; c.out_ld = C; c.res_ld = C;
+      c.in = X0; c.out = X1; c.relu = 0; c.res = nullptr;
+      ORCA_TRY(conv(Lk[1], c, s));  // lout_k
+      c.in = X1; c.out = X0; c.relu = 1;
+      ORCA_TRY(conv(Lk[2], c, s));
+      if (k < 6) {
+        c.in = X0; c.out = X2; c.relu = 1; c.res = X1;  // out_k + lout_k
+        ORCA_TRY(conv(Lk[3], c, s));
+        ORCA_TRY(add_maxpool1d(X2, nullptr, Pb, nb, len, C, kPool[k + 1], s));
+      } else {
+        c.in = X0; c.out = out7; c.relu = 1; c.res = nullptr;  // out7 only (orca_modules.py:949-950)
+        ORCA_TRY(conv(Lk[3], c, s));
+      }
+    }
+  }
+  ar.release(m);
+  return ORCA_B200_OK;
+}
+
+static const int64_t kBin = 4000, kHaloBins = 28;  // x_padding = 112000, orca_modules.py:931-932
+static const int64_t kDefaultChunkBp = 4000000;
+
+static int encoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                       int64_t sL, float* out, int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, Arena& ar,
+                       cudaStream_t s) {
+  const int64_t P = L / kBin;
+  if (chunk_bp <= 0) chunk_bp = kDefaultChunkBp;
+  int64_t chunk_bins = chunk_bp / kBin;
+  if (chunk_bins < 1) chunk_bins = 1;
+  const int64_t span = bin_end - bin_begin;
+  if (span <= 0) return ORCA_B200_OK;
+  // group several samples per pass when a whole sample fits in one chunk
+  int64_t group = 1;
+  if (span <= chunk_bins) { group = chunk_bins / span; if (group > B) group = B; if (group < 1) group = 1; }
+  for (int64_t b0 = 0; b0 < B; b0 += group) {
+    const int nb = (int)((B - b0 < group) ? (B - b0) : group);
+    for (int64_t cb = bin_begin; cb < bin_end; cb += chunk_bins) {
+      const int64_t ce = (cb + chunk_bins < bin_end) ? cb + chunk_bins : bin_end;
+      const int64_t hb = (cb - kHaloBins > 0) ? cb - kHaloBins : 0;
+      const int64_t he = (ce + kHaloBins < P) ? ce + kHaloBins : P;
+      const int64_t n = (he - hb) * kBin;
+      const size_t mk = ar.mark();
+      float* o7 = ar.f32((size_t)nb * (he - hb) * 128);
+      ARENA_OK(ar);
+      ORCA_TRY(encoder_window(m->L.data(), x + b0 * sB, sB, sC, sL, nb, L, hb * kBin, n, o7, ar, s));
+      if (!ar.dry) {
+        ORCA_CUDA_OK(cudaMemcpy2DAsync(out + (b0 * P + cb) * 128, (size_t)P * 128 * sizeof(float),
+                                       o7 + (cb - hb) * 128, (size_t)(he - hb) * 128 * sizeof(float),
+                                       (size_t)(ce - cb) * 128 * sizeof(float), (size_t)nb,
+                                       cudaMemcpyDeviceToDevice, s));
+      }
+      ar.release(mk);
+    }
+  }
+  return ORCA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Encoder2 / Encoder2b / Encoder3  (orca_modules.py:1151-1169, :1266-1276, :1388-1406)
+// ---------------------------------------------------------------------------------------------
+static int unet_run(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
+                    int64_t sL, float* const* outs, int n_out, int coarsest_only, Arena& ar, cudaStream_t s) {
+  const int n = n_out - 1;
+  const bool has_up = m->kind != ORCA_B200_ENCODER2B;
+  const bool direct = !has_up;  // Encoder2b returns the pooling-half tensors themselves
+  const ConvLayer* Ll = m->L.data();           // lblocks
+  const ConvLayer* Lb = Ll + 2 * n;            // blocks
+  const ConvLayer* Ldl = Lb + 2 * n;           // downlblocks
+  const ConvLayer* Ldb = Ldl + 2 * n;          // downblocks
+  const size_t mk = ar.mark();
+  const int nb = (int)B;
+  std::vector<float*> enc(n + 1);
+  const size_t full = (size_t)B * P * 128;
+  // level-0 tensor (channel-last copy of x)
+  enc[0] = (direct && !coarsest_only) ? (ar.dry ? nullptr : outs[0]) : ar.f32(full);
+  float* T0 = ar.f32(full);
+  float* T1 = ar.f32(full);
+  float* Pb = ar.f32(full);
+  for (int i = 1; i <= n; ++i) {
+    const bool to_out = (i == n) || (direct && !coarsest_only);
+    enc[i] = to_out ? (ar.dry ? nullptr : outs[i]) : ar.f32(full >> i);
+  }
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    ORCA_TRY(to_channel_last(x, sB, sC, sL, enc[0], nb, 128, P, s));
+    ConvCall c;
+    c.B = nb; c.H = 1; c.in_ld = c.out_ld = c.res_ld = 128;
+    int64_t len = P;
+    for (int i = 0; i < n; ++i) {  // pooling half
+      ORCA_TRY(add_maxpool1d(enc[i], nullptr, Pb, nb, len, 128, 2, s));
+      len >>= 1;
+      c.W = (int)len;
+      c.in = Pb; c.out = T0; c.relu = 0; c.res = nullptr; c.res2 = nullptr;
+      ORCA_TRY(conv(Ll[2 * i], c, s));
+      c.in = T0; c.out = T1;
+      ORCA_TRY(conv(Ll[2 * i + 1], c, s));  // lout
+      c.in = T1; c.out = T0; c.relu = 1;
+      ORCA_TRY(conv(Lb[2 * i], c, s));
+      c.in = T0; c.out = enc[i + 1]; c.res = T1;  // out = conv(lout) + lout
+      ORCA_TRY(conv(Lb[2 * i + 1], c, s));
+    }
+    if (has_up && !coarsest_only) {
+      const float* cur = enc[n];
+      for (int j = 0; j < n; ++j) {  // upsampling half, skip connections in reverse
+        const int lvl = n - 1 - j;
+        ORCA_TRY(upsample2_1d(cur, Pb, nb, len, 128, s));
+        len <<= 1;
+        c.W = (int)len;
+        c.in = Pb; c.out = T0; c.relu = 0; c.res = nullptr; c.res2 = nullptr;
+        ORCA_TRY(conv(Ldl[2 * j], c, s));
+        c.in = T0; c.out = T1;
+        ORCA_TRY(conv(Ldl[2 * j + 1], c, s));  // lout
+        c.in = T1; c.out = T0; c.relu = 1;
+        ORCA_TRY(conv(Ldb[2 * j], c, s));
+        c.in = T0; c.out = outs[lvl]; c.res = T1; c.res2 = enc[lvl];  // conv(lout) + lout, + skip
+        ORCA_TRY(conv(Ldb[2 * j + 1], c, s));
+        cur = outs[lvl];
+      }
+    }
+  }
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder / Decoder_1m bodies.  orca_modules.py:461-488 and :782-800.
+// `mat128` is the outer-sum lift [B][S][S][128]; the result lands in out (B,1,S,S).
+// ---------------------------------------------------------------------------------------------
+struct Rot3 {
+  float* t[3];
+  int cur = 0;
+  float* next() { cur = (cur + 1) % 3; return t[cur]; }
+};
+
+// one residual bottleneck unit:  cur = lm(cur) [+ cur] ; cur = m(cur) + cur
+static int bottleneck(const ConvLayer* lm, const ConvLayer* mm, const float*& cur, int cur_ld, bool l_residual,
+                      Rot3& rot, float* Hbuf, int B, int S, cudaStream_t s) {
+  ConvCall c;
+  c.B = B; c.H = S; c.W = S;
+  c.in = cur; c.in_ld = cur_ld; c.out = Hbuf; c.out_ld = lm[0].c_out; c.relu = 0;
+  ORCA_TRY(conv(lm[0], c, s));
+  float* t1 = rot.next();
+  c.in = Hbuf; c.in_ld = lm[0].c_out; c.out = t1; c.out_ld = 64; c.res_ld = 64;
+  c.res = l_residual ? cur : nullptr;
+  ORCA_TRY(conv(lm[1], c, s));
+  c.in = t1; c.in_ld = 64; c.out = Hbuf; c.out_ld = mm[0].c_out; c.relu = 1; c.res = nullptr;
+  ORCA_TRY(conv(mm[0], c, s));
+  float* t2 = rot.next();
+  c.in = Hbuf; c.in_ld = mm[0].c_out; c.out = t2; c.out_ld = 64; c.res = t1;
+  ORCA_TRY(conv(mm[1], c, s));
+  cur = t2;
+  return ORCA_B200_OK;
+}
+
+static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl /*[B][S][128]*/,
+                        int B, int S, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
+                        int64_t ysB, int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+  const size_t mk = ar.mark();
+  const size_t pix = (size_t)B * S * S;
+  float* mat = ar.f32(pix * 128);
+  Rot3 rot;
+  rot.t[0] = ar.f32(pix * 64);
+  rot.t[1] = ar.f32(pix * 64);
+  rot.t[2] = ar.f32(pix * 64);
+  float* Hbuf = ar.f32(pix * 64);
+  float* E = is_1m ? nullptr : ar.f32(pix * 64);
+  float* tmp = ar.f32(pix);
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    ORCA_TRY(outer_sum(xcl, mat, B, 128, S, s));
+    const float* cur = nullptr;
+    if (is_1m) {
+      cur = mat;  // first unit: 128 -> 32 -> 64, no residual on lm (orca_modules.py:789-792)
+      ORCA_TRY(bottleneck(L + D1M_LCONV, L + D1M_CONV, cur, 128, false, rot, Hbuf, B, S, s));
+      for (int i = 1; i < 19; ++i)
+        ORCA_TRY(bottleneck(L + D1M_LCONV + 2 * i, L + D1M_CONV + 2 * i, cur, 64, true, rot, Hbuf, B, S, s));
+      ORCA_TRY(final_head(cur, L[D1M_FINAL], L[D1M_FINAL + 1], tmp, out, B, S, s));
+    } else {
+      ConvCall c;
+      c.B = B; c.H = S; c.W = S; c.res_ld = 64;
+      // mat = lcombinerD(cat(mat, distenc)) ; mat = combinerD(mat) + mat      (:463-465)
+      ORCA_TRY(extra_channel_conv(distenc, dsB, dsH, dsW, L[DEC_LCOMBD].w_extra, E, B, S, 64, 0, s));
+      float* a0 = rot.next();
+      c.in = mat; c.in_ld = 128; c.out = a0; c.out_ld = 64; c.relu = 0; c.res = E;
+      ORCA_TRY(conv(L[DEC_LCOMBD], c, s));
+      float* a1 = rot.next();
+      c.in = a0; c.in_ld = 64; c.out = a1; c.res = nullptr;
+      ORCA_TRY(conv(L[DEC_LCOMBD + 1], c, s));
+      float* a2 = rot.next();
+      c.in = a1; c.out = a2; c.relu = 1;
+      ORCA_TRY(conv(L[DEC_COMBD], c, s));
+      float* a3 = rot.next();  // == a0's buffer, free by now
+      c.in = a2; c.out = a3; c.res = a1;
+      ORCA_TRY(conv(L[DEC_COMBD + 1], c, s));
+      cur = a3;
+      if (y) {
+        // cur = lcombiner(cat(mat, upsample(y))) ; cur = combiner(cur) + cur   (:467-474)
+        const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
+        ORCA_TRY(extra_channel_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, E, B, S, 64, mode, s));
+        float* b0 = rot.next();
+        c.in = cur; c.out = b0; c.relu = 0; c.res = E;
+        ORCA_TRY(conv(L[DEC_LCOMB], c, s));
+        float* b1 = rot.next();
+        c.in = b0; c.out = b1; c.res = nullptr;
+        ORCA_TRY(conv(L[DEC_LCOMB + 1], c, s));
+        float* b2 = rot.next();
+        c.in = b1; c.out = b2; c.relu = 1;
+        ORCA_TRY(conv(L[DEC_COMB], c, s));
+        float* b3 = rot.next();
+        c.in = b2; c.out = b3; c.res = b1;
+        ORCA_TRY(conv(L[DEC_COMB + 1], c, s));
+        cur = b3;
+      } else {
+        // cur = lconvtwos[0](cur) ; cur = convtwos[0](cur) + cur               (:475-477)
+        ORCA_TRY(bottleneck(L + DEC_LCONV, L + DEC_CONV, cur, 64, false, rot, Hbuf, B, S, s));
+      }
+      for (int i = 1; i < 28; ++i)  // (:479-485)
+        ORCA_TRY(bottleneck(L + DEC_LCONV + 2 * i, L + DEC_CONV + 2 * i, cur, 64, true, rot, Hbuf, B, S, s));
+      ORCA_TRY(final_head(cur, L[DEC_FINAL], L[DEC_FINAL + 1], tmp, out, B, S, s));
+    }
+  }
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+static int decoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t S, int64_t xsB, int64_t xsC,
+                       int64_t xsL, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
+                       int64_t ysB, int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+  const size_t mk = ar.mark();
+  float* xcl = ar.f32((size_t)B * S * 128);
+  ARENA_OK(ar);
+  if (!ar.dry) ORCA_TRY(to_channel_last(x, xsB, xsC, xsL, xcl, (int)B, 128, S, s));
+  ORCA_TRY(decoder_body(m, m->L.data(), m->kind == ORCA_B200_DECODER_1M, xcl, (int)B, (int)S, distenc, dsB, dsH,
+                        dsW, y, ysB, ysH, ysW, out, ar, s));
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+// Net.forward (orca_modules.py:1833-1900): encoder body (monolithic) + Decoder_1m body [+ final_1d]
+static int net_run(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                   int64_t sL, float* out, float* out_1d, Arena& ar, cudaStream_t s) {
+  const int64_t S = L / kBin;
+  const size_t mk = ar.mark();
+  float* o7 = ar.f32((size_t)B * S * 128);
+  ARENA_OK(ar);
+  for (int64_t b = 0; b < B; ++b)
+    ORCA_TRY(encoder_window(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
+  ORCA_TRY(decoder_body(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, nullptr, 0, 0, 0, nullptr, 0, 0, 0, out, ar, s));
+  if (m->num_1d > 0 && out_1d) {  // final_1d (orca_modules.py:1824-1830, :1852-1853)
+    float* h = ar.f32((size_t)B * S * 128);
+    ARENA_OK(ar);
+    if (!ar.dry) {
+      const ConvLayer* F = m->L.data() + ENC_N + D1M_N;
+      ConvCall c;
+      c.B = (int)B; c.H = 1; c.W = (int)S; c.in = o7; c.in_ld = 128; c.out = h; c.out_ld = 128; c.relu = 1;
+      ORCA_TRY(conv_simt(F[0], c, s));
+      ORCA_TRY(head_1d_sigmoid(h, F[1], out_1d, (int)B, (int)S, s));
+    }
+  }
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// module creation: fold BN, pack, upload
+// ---------------------------------------------------------------------------------------------
+static int upload(const std::vector<float>& h, float** d, std::vector<void*>& allocs) {
+  void* p = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(float) + 16));
+  allocs.push_back(p);
+  ORCA_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *d = static_cast<float*>(p);
+  return ORCA_B200_OK;
+}
+
+static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<void*>& allocs) {
+  const int taps = p.kh * p.kw;
+  const bool odd = (p.c_in == 129 || p.c_in == 65);
+  const int cin_main = odd ? p.c_in - 1 : p.c_in;
+  L.c_in = cin_main; L.c_out = p.c_out; L.kh = p.kh; L.kw = p.kw; L.dil = p.dilation;
+  std::vector<double> scale(p.c_out, 1.0), shift(p.c_out, 0.0);
+  const bool bn = p.bn_weight && p.bn_bias && p.bn_mean && p.bn_var;
+  for (int co = 0; co < p.c_out; ++co) {
+    const double b = p.bias ? (double)p.bias[co] : 0.0;
+    if (bn) {  // y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
+      const double sc = (double)p.bn_weight[co] / std::sqrt((double)p.bn_var[co] + (double)p.bn_eps);
+      scale[co] = sc;
+      shift[co] = (b - (double)p.bn_mean[co]) * sc + (double)p.bn_bias[co];
+    } else {
+      shift[co] = b;
+    }
+  }
+  std::vector<float> w((size_t)taps * cin_main * p.c_out), bias(p.c_out), wx;
+  if (odd) wx.resize((size_t)taps * p.c_out);
+  for (int co = 0; co < p.c_out; ++co) {
+    bias[co] = (float)shift[co];
+    for (int ci = 0; ci < p.c_in; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float v = (float)((double)p.weight[((size_t)co * p.c_in + ci) * taps + t] * scale[co]);
+        if (ci < cin_main) w[((size_t)t * cin_main + ci) * p.c_out + co] = v;
+        else wx[(size_t)t * p.c_out + co] = v;
+      }
+  }
+  ORCA_TRY(upload(w, &L.w, allocs));
+  ORCA_TRY(upload(bias, &L.b, allocs));
+  if (odd) ORCA_TRY(upload(wx, &L.w_extra, allocs));
+  ORCA_TRY(tc_pack_layer(L, w.data(), allocs));
+  return ORCA_B200_OK;
+}
+
+static int check_ptr_device(const void* p, const char* what) {
+  if (!p) { set_error("%s is NULL", what); return ORCA_B200_EINVAL; }
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("%s: cudaPointerGetAttributes failed", what); return ORCA_B200_ECUDA; }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+    set_error("%s is not a device pointer (liborca_b200 has no CPU path)", what);
+    return ORCA_B200_EINVAL;
+  }
+  return ORCA_B200_OK;
+}
+
+}  // namespace orca
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* orca_b200_version(void) { return "orca_b200 0.1 (sm_100a)"; }
+const char* orca_b200_last_error(void) { return t_error.c_str(); }
+uint64_t orca_b200_launch_count(void) { return g_launches.load(); }
+int orca_b200_get_impl(void) { return g_impl.load(); }
+int orca_b200_set_impl(int impl) {
+  if (impl < ORCA_B200_IMPL_AUTO || impl > ORCA_B200_IMPL_TC) { set_error("set_impl: unknown impl %d", impl); return ORCA_B200_EINVAL; }
+  g_impl.store(impl);
+  return ORCA_B200_OK;
+}
+
+int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_t n_convs, uint32_t flags,
+                            int32_t num_1d, orca_b200_module** out) {
+  if (!convs || !out) { set_error("module_create: NULL argument"); return ORCA_B200_EINVAL; }
+  *out = nullptr;
+  std::vector<Spec> spec;
+  switch (kind) {
+    case ORCA_B200_ENCODER: spec_encoder(spec); break;
+    case ORCA_B200_ENCODER2: spec_unet(spec, 5, true); break;
+    case ORCA_B200_ENCODER2B: spec_unet(spec, 5, false); break;
+    case ORCA_B200_ENCODER3: spec_unet(spec, 3, true); break;
+    case ORCA_B200_DECODER: spec_decoder(spec); break;
+    case ORCA_B200_DECODER_1M: spec_decoder_1m(spec); break;
+    case ORCA_B200_NET:
+      spec_encoder(spec);
+      spec_decoder_1m(spec);
+      if (num_1d > 0) { spec.push_back({128, 128, 1, 1, 1}); spec.push_back({128, num_1d, 1, 1, 1}); }
+      break;
+    default: set_error("module_create: unknown module kind %d", kind); return ORCA_B200_EINVAL;
+  }
+  if (num_1d < 0 || (kind != ORCA_B200_NET && num_1d != 0)) { set_error("module_create: num_1d=%d invalid for kind %d", num_1d, kind); return ORCA_B200_EINVAL; }
+  if ((size_t)n_convs != spec.size()) {
+    set_error("module_create: kind %d expects %zu convolutions, got %d", kind, spec.size(), n_convs);
+    return ORCA_B200_EINVAL;
+  }
+  for (int i = 0; i < n_convs; ++i) {
+    const orca_b200_conv_params& p = convs[i];
+    const Spec& e = spec[i];
+    if (p.c_in != e.c_in || p.c_out != e.c_out || p.kh != e.kh || p.kw != e.kw || p.dilation != e.dil) {
+      set_error("module_create: conv %d is (%d->%d, %dx%d, d=%d) but kind %d expects (%d->%d, %dx%d, d=%d)", i, p.c_in,
+                p.c_out, p.kh, p.kw, p.dilation, kind, e.c_in, e.c_out, e.kh, e.kw, e.dil);
+      return ORCA_B200_EINVAL;
+    }
+    if (!p.weight) { set_error("module_create: conv %d has no weight", i); return ORCA_B200_EINVAL; }
+    const int nbn = (p.bn_weight != nullptr) + (p.bn_bias != nullptr) + (p.bn_mean != nullptr) + (p.bn_var != nullptr);
+    if (nbn != 0 && nbn != 4) { set_error("module_create: conv %d has a partial BatchNorm", i); return ORCA_B200_EINVAL; }
+  }
+  orca_b200_module* m = new (std::nothrow) orca_b200_module();
+  if (!m) { set_error("module_create: out of host memory"); return ORCA_B200_EINVAL; }
+  m->kind = kind; m->flags = flags; m->num_1d = num_1d;
+  if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); delete m; set_error("module_create: no CUDA device"); return ORCA_B200_ECUDA; }
+  m->L.resize(n_convs);
+  for (int i = 0; i < n_convs; ++i) {
+    int st = pack_layer(convs[i], m->L[i], m->allocs);
+    if (st != ORCA_B200_OK) { orca_b200_module_destroy(m); return st; }
+  }
+  *out = m;
+  return ORCA_B200_OK;
+}
+
+void orca_b200_module_destroy(orca_b200_module* m) {
+  if (!m) return;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int orca_b200_module_kind(const orca_b200_module* m) { return m ? m->kind : 0; }
+
+// ---- Encoder -----------------------------------------------------------------------------------
+static int encoder_args_ok(const orca_b200_module* m, int64_t B, int64_t L, int64_t b0, int64_t b1) {
+  if (!m || m->kind != ORCA_B200_ENCODER) { set_error("encoder: module is not an Encoder"); return ORCA_B200_EINVAL; }
+  if (B <= 0 || L <= 0 || L % kBin != 0) { set_error("encoder: B=%lld, L=%lld (L must be a positive multiple of 4000)", (long long)B, (long long)L); return ORCA_B200_EINVAL; }
+  if (b0 < 0 || b1 > L / kBin || b0 > b1) { set_error("encoder: bin range [%lld, %lld) outside [0, %lld)", (long long)b0, (long long)b1, (long long)(L / kBin)); return ORCA_B200_EINVAL; }
+  return ORCA_B200_OK;
+}
+
+size_t orca_b200_encoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L, int64_t chunk_bp) {
+  if (encoder_args_ok(m, B, L, 0, L / kBin) != ORCA_B200_OK) return 0;
+  Arena ar; ar.dry = true;
+  encoder_run(m, nullptr, B, L, 0, 0, 0, nullptr, 0, L / kBin, chunk_bp, ar, nullptr);
+  return ar.peak + 256;
+}
+
+int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                              int64_t sL, int64_t x_pos0, int64_t x_len, float* out, int64_t bin_begin,
+                              int64_t bin_end, int64_t chunk_bp, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  ORCA_TRY(encoder_args_ok(m, B, L, bin_begin, bin_end));
+  ORCA_TRY(check_ptr_device(x, "encoder: x"));
+  ORCA_TRY(check_ptr_device(out, "encoder: out"));
+  ORCA_TRY(check_ptr_device(workspace, "encoder: workspace"));
+  {  // the window x covers must contain everything the requested bins read
+    int64_t need0 = bin_begin * kBin - kHaloBins * kBin - 4, need1 = bin_end * kBin + kHaloBins * kBin + 4;
+    if (need0 < 0) need0 = 0;
+    if (need1 > L) need1 = L;
+    if (x_pos0 < 0 || x_len <= 0 || (bin_begin < bin_end && (x_pos0 > need0 || x_pos0 + x_len < need1))) {
+      set_error("encoder: input window [%lld, %lld) does not cover [%lld, %lld) needed for bins [%lld, %lld)",
+                (long long)x_pos0, (long long)(x_pos0 + x_len), (long long)need0, (long long)need1,
+                (long long)bin_begin, (long long)bin_end);
+      return ORCA_B200_EINVAL;
+    }
+  }
+  Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
+  // virtual base: position l of the sequence lives at x + (l - x_pos0) * sL
+  return encoder_run(m, x - x_pos0 * sL, B, L, sB, sC, sL, out, bin_begin, bin_end, chunk_bp, ar,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// ---- Encoder2 / 2b / 3 -------------------------------------------------------------------------
+static int unet_args_ok(const orca_b200_module* m, int64_t B, int64_t P, int n_out) {
+  if (!m || (m->kind != ORCA_B200_ENCODER2 && m->kind != ORCA_B200_ENCODER2B && m->kind != ORCA_B200_ENCODER3)) {
+    set_error("encoder2: module is not an Encoder2/Encoder2b/Encoder3"); return ORCA_B200_EINVAL;
+  }
+  const int want = m->kind == ORCA_B200_ENCODER3 ? 4 : 6;
+  if (n_out != want) { set_error("encoder2: n_out=%d, module kind %d returns %d tensors", n_out, m->kind, want); return ORCA_B200_EINVAL; }
+  if (B <= 0 || P <= 0 || P % (1 << (want - 1)) != 0) { set_error("encoder2: B=%lld P=%lld (P must be a positive multiple of %d)", (long long)B, (long long)P, 1 << (want - 1)); return ORCA_B200_EINVAL; }
+  return ORCA_B200_OK;
+}
+
+size_t orca_b200_encoder2_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t P) {
+  if (!m) return 0;
+  const int n_out = m->kind == ORCA_B200_ENCODER3 ? 4 : 6;
+  if (unet_args_ok(m, B, P, n_out) != ORCA_B200_OK) return 0;
+  Arena ar; ar.dry = true;
+  // worst case = coarsest_only (nothing lands in caller buffers)
+  unet_run(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 1, ar, nullptr);
+  size_t a = ar.peak;
+  Arena ar2; ar2.dry = true;
+  unet_run(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 0, ar2, nullptr);
+  return (a > ar2.peak ? a : ar2.peak) + 256;
+}
+
+int orca_b200_encoder2_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
+                               int64_t sL, float* const* outs, int32_t n_out, int32_t coarsest_only, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  ORCA_TRY(unet_args_ok(m, B, P, n_out));
+  if (!outs) { set_error("encoder2: outs is NULL"); return ORCA_B200_EINVAL; }
+  ORCA_TRY(check_ptr_device(x, "encoder2: x"));
+  ORCA_TRY(check_ptr_device(workspace, "encoder2: workspace"));
+  for (int i = 0; i < n_out; ++i)
+    if (!coarsest_only || i == n_out - 1) ORCA_TRY(check_ptr_device(outs[i], "encoder2: outs[i]"));
+  Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
+  return unet_run(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, static_cast<cudaStream_t>(stream));
+}
+
+// ---- Decoder / Decoder_1m ----------------------------------------------------------------------
+static int decoder_args_ok(const orca_b200_module* m, int64_t B, int64_t S) {
+  if (!m || (m->kind != ORCA_B200_DECODER && m->kind != ORCA_B200_DECODER_1M)) { set_error("decoder: module is not a Decoder/Decoder_1m"); return ORCA_B200_EINVAL; }
+  if (B <= 0 || S <= 0 || S > 4096) { set_error("decoder: B=%lld S=%lld out of range", (long long)B, (long long)S); return ORCA_B200_EINVAL; }
+  return ORCA_B200_OK;
+}
+
+size_t orca_b200_decoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t S) {
+  if (decoder_args_ok(m, B, S) != ORCA_B200_OK) return 0;
+  Arena ar; ar.dry = true;
+  decoder_run(m, nullptr, B, S, 0, 0, 0, nullptr, 0, 0, 0, nullptr, 0, 0, 0, nullptr, ar, nullptr);
+  return ar.peak + 256;
+}
+
+int orca_b200_decoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t S, int64_t xsB, int64_t xsC,
+                              int64_t xsL, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
+                              int64_t ysB, int64_t ysH, int64_t ysW, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  ORCA_TRY(decoder_args_ok(m, B, S));
+  ORCA_TRY(check_ptr_device(x, "decoder: x"));
+  ORCA_TRY(check_ptr_device(out, "decoder: out"));
+  ORCA_TRY(check_ptr_device(workspace, "decoder: workspace"));
+  if (m->kind == ORCA_B200_DECODER) {
+    ORCA_TRY(check_ptr_device(distenc, "decoder: distenc"));
+    if (y) {
+      ORCA_TRY(check_ptr_device(y, "decoder: y"));
+      if (S % 2) { set_error("decoder: S must be even when a coarse prediction is given"); return ORCA_B200_EINVAL; }
+    }
+  } else if (distenc || y) {
+    set_error("decoder: Decoder_1m takes neither distenc nor y"); return ORCA_B200_EINVAL;
+  }
+  Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
+  return decoder_run(m, x, B, S, xsB, xsC, xsL, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// ---- Net ---------------------------------------------------------------------------------------
+static int net_args_ok(const orca_b200_module* m, int64_t B, int64_t L) {
+  if (!m || m->kind != ORCA_B200_NET) { set_error("net: module is not a Net"); return ORCA_B200_EINVAL; }
+  if (B <= 0 || L <= 0 || L % kBin != 0 || L / kBin > 4096) { set_error("net: B=%lld L=%lld invalid", (long long)B, (long long)L); return ORCA_B200_EINVAL; }
+  return ORCA_B200_OK;
+}
+
+size_t orca_b200_net_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L) {
+  if (net_args_ok(m, B, L) != ORCA_B200_OK) return 0;
+  Arena ar; ar.dry = true;
+  float dummy;
+  net_run(m, nullptr, B, L, 0, 0, 0, nullptr, &dummy, ar, nullptr);
+  return ar.peak + 256;
+}
+
+int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                          int64_t sL, float* out, float* out_1d, void* workspace, size_t workspace_bytes, void* stream) {
+  ORCA_TRY(net_args_ok(m, B, L));
+  ORCA_TRY(check_ptr_device(x, "net: x"));
+  ORCA_TRY(check_ptr_device(out, "net: out"));
+  ORCA_TRY(check_ptr_device(workspace, "net: workspace"));
+  if (out_1d) ORCA_TRY(check_ptr_device(out_1d, "net: out_1d"));
+  Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
+  return net_run(m, x, B, L, sB, sC, sL, out, out_1d, ar, static_cast<cudaStream_t>(stream));
+}
+
+// ---- profiling -------------------------------------------------------------------------------
+int orca_b200_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_profile.store(on ? 1 : 0);
+  return ORCA_B200_OK;
+}
+
+int64_t orca_b200_profile_summary(char* buf, int64_t cap) {
+  struct Agg { int c_in, c_out, taps, dil, tc; long n; double ms, flop; };
+  std::vector<Agg> aggs;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("profile_summary: event query failed");
+      return ORCA_B200_ECUDA;
+    }
+    Agg* a = nullptr;
+    for (auto& x : aggs)
+      if (x.c_in == r.c_in && x.c_out == r.c_out && x.taps == r.taps && x.dil == r.dil && x.tc == r.tc) { a = &x; break; }
+    if (!a) { aggs.push_back({r.c_in, r.c_out, r.taps, r.dil, r.tc, 0, 0.0, 0.0}); a = &aggs.back(); }
+    a->n += 1; a->ms += ms; a->flop += r.flop;
+  }
+  std::string js = "[";
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof line, "%s{\"c_in\":%d,\"c_out\":%d,\"taps\":%d,\"dil\":%d,\"tc\":%d,\"launches\":%ld,\"ms\":%.6f,\"flop\":%.6e}",
+             i ? "," : "", aggs[i].c_in, aggs[i].c_out, aggs[i].taps, aggs[i].dil, aggs[i].tc, aggs[i].n, aggs[i].ms, aggs[i].flop);
+    js += line;
+  }
+  js += "]";
+  if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", js.c_str()); }
+  return (int64_t)js.size() + 1;
+}
+
+// ---- background ------------------------------------------------------------------------------
+int orca_b200_background_forward(const double* normmat, int64_t n, int64_t r0, int64_t f, int64_t S, int32_t flip,
+                                 float* out, void* stream) {
+  ORCA_TRY(check_ptr_device(normmat, "background: normmat"));
+  ORCA_TRY(check_ptr_device(out, "background: out"));
+  return background_level(normmat, n, r0, f, S, flip, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""
+Multi-GPU forward: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).
+
+The Encoder is >85 % of a pass and shards along the sequence: rank r owns the
+4 kb bins [r*P/R, (r+1)*P/R) and needs the input bp of that span plus the 112 kb halo the
+reference's own block overlap uses (orca_modules.py:931-932) -- every rank slices its window
+out of the host copy, so there is no input exchange at all.  The one real exchange step is an
+all-gather of the (P/R, 128) fp32 encodings (0.5 MB per rank at 32 Mb, 4.1 MB at 256 Mb), after
+which Encoder2/Encoder3 and the decoder cascades (<12 % of the FLOPs, global receptive field) run
+un-sharded: the forward-strand cascade on rank 0, the reverse-complement cascade on rank 1.
+
+For the reverse strand a rank encodes the MIRRORED bins [P-b1, P-b0): they read exactly the same
+forward-strand window walked backwards, so one upload serves both strands.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import predict
+
+HALO_BP = 112000 + 4000  # the encoder's 112 kb halo (+1 bin of slack for the k=9 taps at the edge)
+
+
+def shard_bins(P, rank, world):
+    """Contiguous, near-equal bin ranges; equal when world divides P (8000 and 64000 / 1,2,4,8)."""
+    base, rem = divmod(P, world)
+    b0 = rank * base + min(rank, rem)
+    return b0, b0 + base + (1 if rank < rem else 0)
+
+
+def shard_window(L, b0, b1):
+    """Forward-strand bp window a shard must hold to encode bins [b0, b1) (and their mirror)."""
+    return max(b0 * 4000 - HALO_BP, 0), min(b1 * 4000 + HALO_BP, L)
+
+
+class ShardedForward:
+    """32 Mb genomepredict-equivalent forward of one shell, sequence-sharded over `world` ranks."""
+
+    def __init__(self, shell, L, rank=0, world=1, device=None):
+        self.shell, self.L, self.rank, self.world = shell, L, rank, world
+        self.device = device if device is not None else predict._device_of(shell)
+        self.P = L // 4000
+        if world > 1 and self.P % world != 0:
+            raise ValueError("number of 4 kb bins (%d) must be divisible by the world size (%d)" % (self.P, world))
+        self.b0, self.b1 = shard_bins(self.P, rank, world)
+        self.s0, self.s1 = shard_window(L, self.b0, self.b1)
+        self.window = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
+
+    def upload(self, seq_host):
+        """seq_host: (1, L, 4) float32 CPU tensor (pinned for full-speed copies); uploads this rank's window."""
+        sl = seq_host[:, self.s0:self.s1, :]
+        self.window = sl.to(self.device, non_blocking=True)
+        self.h2d_bytes = sl.numel() * 4
+        return self.window
+
+    def _encode(self, reverse):
+        P, n = self.P, self.b1 - self.b0
+        enc = torch.empty((1, P, 128), dtype=torch.float32, device=self.device)
+        bins = (P - self.b1, P - self.b0) if reverse else (self.b0, self.b1)
+        self.shell.net0(self.window.transpose(1, 2), bin_range=bins, out=enc, reverse_complement=reverse,
+                        window=(self.s0, self.L))
+        if self.world > 1:
+            mine = enc[0, bins[0]:bins[1]].contiguous()
+            gathered = torch.empty((self.world * n, 128), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(gathered, mine)  # concatenation along dim 0 (NCCL and gloo agree)
+            gathered = gathered.view(self.world, n, 128)
+            if reverse:  # rank r holds the mirrored range -> chunk order is reversed
+                gathered = torch.flip(gathered, [0])
+            enc = gathered.reshape(1, P, 128)
+        return enc.transpose(1, 2)
+
+    def forward(self, mpos, wpos):
+        """Returns the 6 strand-averaged maps (6, 250, 250) on rank 0 (None elsewhere)."""
+        shell, world, rank = self.shell, self.world, self.rank
+        with torch.no_grad():
+            enc_f = self._encode(False)
+            enc_r = self._encode(True)
+            rev_rank = 1 if world > 1 else 0
+            preds = {}
+            for reverse, owner, enc in ((False, 0, enc_f), (True, rev_rank, enc_r)):
+                if rank == owner:
+                    encs = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc)))
+                    p, _ = predict.cascade_32mb(shell, encs, 1, mpos, wpos, reverse)
+                    preds[reverse] = torch.cat([t[0] for t in p], 0)  # (6, 250, 250)
+            if world > 1:
+                if rank == rev_rank:
+                    dist.send(preds[True], dst=0)
+                elif rank == 0:
+                    buf = torch.empty((6, 250, 250), dtype=torch.float32, device=self.device)
+                    dist.recv(buf, src=rev_rank)
+                    preds[True] = buf
+            if rank != 0:
+                return None
+            return 0.5 * preds[False] + 0.5 * torch.flip(preds[True], [1, 2])

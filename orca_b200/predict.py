@@ -1,0 +1,203 @@
+"""
+B200-side multiscale drivers: the same call contract and return dict as
+`orca_predict.genomepredict` (orca_predict.py:231-540) and `genomepredict_256Mb` (:543-878),
+restated for the native modules so that a pass costs ONE host->device upload:
+
+  * the sequence is uploaded once; the reverse-complement strand is read in place (the RC of a
+    (L,4) one-hot array is the same buffer walked backwards, orca_predict.py:324-329), instead
+    of `sequence[:, ::-1, ::-1].copy()` + a second upload per model;
+  * `log(normmats[level])` lives on the device per shell (the reference re-uploads it on every
+    eval_step, :349-353); the 256 Mb background levels are block-averaged on the GPU
+    (orca_b200_background_forward) instead of float64 numpy on the host (:724-737);
+  * strand averaging `0.5*fwd + 0.5*rev[::-1, ::-1]` (:510-523) happens on the device and the
+    maps come back in one device->host copy.
+
+The unmodified reference drivers also work with these shells (`models=[shell]`), because the
+modules keep the reference signatures; this file is the fast path, not a requirement.
+`targets` / `annotation` (plot-only bookkeeping) are out of scope.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _device_of(model):
+    for p in model.parameters():
+        return p.device
+    raise RuntimeError("model has no parameters")
+
+
+def _to_device_sequence(sequence, device):
+    """(B, L, 4) float32 host array (or tensor) -> device tensor, one upload."""
+    if isinstance(sequence, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(sequence, dtype=np.float32))
+    else:
+        t = sequence.float().contiguous()
+    if t.dim() != 3 or t.size(2) != 4:
+        raise ValueError("sequence must be (B, L, 4), got %s" % (tuple(t.shape),))
+    return t.to(device, non_blocking=True)
+
+
+def _log_normmat(model, level, device):
+    cache = model.__dict__.setdefault("_distenc_cache", {})
+    key = (level, str(device))
+    if key not in cache:
+        nm = model.normmats[level]
+        nm = nm[(None,) * (4 - nm.ndim)]  # orca_predict.py:350
+        cache[key] = torch.log(torch.as_tensor(nm, dtype=torch.float32).to(device))
+    return cache[key]
+
+
+def encode_strand(model, seq_dev, reverse):
+    """net0 on one strand of the uploaded (B, L, 4) tensor."""
+    return model.net0(seq_dev.transpose(1, 2), reverse_complement=reverse)
+
+
+def cascade_32mb(model, encodings, batch, mpos, wpos, reverse):
+    """Decoder cascade 32 -> 1 Mb of one (model, strand) (orca_predict.py:348-500)."""
+    device = encodings[1].device
+    preds, starts = [], [0]
+    start_index = 0
+    for j, level in enumerate([32, 16, 8, 4, 2, 1]):
+        distenc = _log_normmat(model, level, device).expand(batch, -1, -1, -1)
+        s = int(starts[j] / level)
+        xl = encodings[level][:, :, s:s + 250]
+        coarse = None if j == 0 else preds[j - 1][:, :, start_index:start_index + 125, start_index:start_index + 125]
+        pred = model.denets[level].forward(xl, distenc, coarse)
+        if level == 1 and j > 0 and hasattr(model, "denet_1_pt"):
+            pred = pred + model.denet_1_pt.forward(xl)
+        if not reverse:
+            start_index = int(np.clip(np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + starts[j] * 4000))
+                                               / (4000 * level)), 0, 125))
+        else:
+            start_index = int(np.clip(np.ceil(((wpos + 16000000 - starts[j] * 4000) - (mpos + level * 1000000 / 4))
+                                              / (4000 * level)), 0, 125))
+        starts.append(starts[j] + start_index * level)
+        preds.append(pred)
+    return preds, starts[:-1]
+
+
+def _average_strands(fwd, rev):
+    """0.5*fwd + 0.5*rev[::-1, ::-1] for batch element 0 (orca_predict.py:510-523)."""
+    out = []
+    for f, r in zip(fwd, rev):
+        a = 0.5 * f[0] + 0.5 * torch.flip(r[0], [1, 2])
+        out.append(a[0] if a.shape[0] == 1 else a)
+    return out
+
+
+def genomepredict(sequence, mchr, mpos=-1, wpos=-1, models=(), targets=None, annotation=None, use_cuda=True,
+                  nan_thresh=1):
+    """Drop-in for orca_predict.genomepredict with native shells (see module docstring)."""
+    if targets is not None or annotation is not None:
+        raise NotImplementedError("targets / annotation are plot-only inputs; use orca_predict.genomepredict for them")
+    if not use_cuda:
+        raise RuntimeError("orca_b200 has no CPU path")
+    models = list(models)
+    if not models or not all(isinstance(m, torch.nn.Module) for m in models):
+        raise ValueError("models must be a non-empty list of shell modules")
+    device = _device_of(models[0])
+    with torch.no_grad(), torch.cuda.device(device):
+        seq_dev = _to_device_sequence(sequence, device)
+        B = seq_dev.shape[0]
+        per_strand, starts0 = [], None
+        for reverse in (False, True):
+            for model in models:
+                encs = dict(zip([1, 2, 4, 8, 16, 32], model.net(encode_strand(model, seq_dev, reverse))))
+                preds, starts = cascade_32mb(model, encs, B, mpos, wpos, reverse)
+                per_strand.append(preds)
+                if not reverse and starts0 is None:
+                    starts0 = starts
+        n = len(models)
+        stacked = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])) for i in range(n)]
+        host = [s.cpu().numpy() for s in stacked]
+    output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
+    output["start_coords"] = [wpos - 16000000 + s * 4000 for s in starts0]
+    output["end_coords"] = [int(output["start_coords"][ii] + 32000000 / 2 ** ii) for ii in range(6)]
+    output["chr"] = mchr
+    output["annos"] = None
+    output["normmats"] = [[m.normmats[ii] for ii in [32, 16, 8, 4, 2, 1]] for m in models]
+    return output
+
+
+def background_level(normmat_dev, r0, f, flip=False, size=250):
+    """log(block-nanmean) of an (n, n) float64 device matrix -> (1, 1, size, size) float32."""
+    out = torch.empty((1, 1, size, size), dtype=torch.float32, device=normmat_dev.device)
+    with torch.cuda.device(normmat_dev.device):
+        _lib.check(_lib.lib().orca_b200_background_forward(
+            normmat_dev.data_ptr(), normmat_dev.shape[0], int(r0), int(f), size, 1 if flip else 0, out.data_ptr(),
+            torch.cuda.current_stream(normmat_dev.device).cuda_stream))
+    return out
+
+
+def cascade_256mb(model, encodings, batch, normmat_dev, chrlen, mpos, wpos, reverse):
+    """Decoder cascade 256 -> 32 Mb of one (model, strand) (orca_predict.py:692-836).
+    Returns (preds, starts, per-level background matrices as float32 device tensors (un-logged))."""
+    preds, starts, ns = [], [0], {}
+    start_index = 0
+    for j, level in enumerate([256, 128, 64, 32]):
+        f = level // 8
+        logbg = background_level(normmat_dev, starts[j], f, flip=False)
+        ns[level] = logbg
+        distenc = (torch.flip(logbg, [2, 3]) if reverse else logbg).expand(batch, -1, -1, -1)
+        s = int(starts[j] / f)
+        xl = encodings[level][:, :, s:s + 250]
+        coarse = None if j == 0 else preds[j - 1][:, :, start_index:start_index + 125, start_index:start_index + 125]
+        pred = model.denets[level].forward(xl, distenc, coarse)
+        if not reverse:
+            proposed = (mpos - level * 1000000 / 4) - (wpos - 128000000 + starts[j] * 4000 * 8)
+        else:
+            proposed = (mpos - level * 1000000 / 4) - (wpos + 128000000 - starts[j] * 4000 * 8 - level * 1000000)
+        if chrlen is not None:
+            bounds = [0 - (wpos - 128000000), chrlen - level * 1000000 / 2 - (wpos - 128000000)]
+            proposed = np.clip(proposed, bounds[0], bounds[1]) if bounds[0] < bounds[1] else bounds[0]
+        start_index = int(np.clip(np.floor(proposed / (4000 * level)), 0, 125))
+        if reverse:
+            start_index = 250 - (start_index + 125)
+        starts.append(starts[j] + start_index * level // 8)
+        preds.append(pred)
+    return preds, starts[:-1], ns
+
+
+def genomepredict_256Mb(sequence, mchr, normmats, chrlen, mpos=-1, wpos=-1, models=(), targets=None, annotation=None,
+                        padding_chr=None, use_cuda=True, nan_thresh=1):
+    """Drop-in for orca_predict.genomepredict_256Mb with native shells."""
+    if targets is not None or annotation is not None:
+        raise NotImplementedError("targets / annotation are plot-only inputs; use orca_predict.genomepredict_256Mb")
+    if not use_cuda:
+        raise RuntimeError("orca_b200 has no CPU path")
+    models = list(models)
+    device = _device_of(models[0])
+    with torch.no_grad(), torch.cuda.device(device):
+        seq_dev = _to_device_sequence(sequence, device)
+        B = seq_dev.shape[0]
+        nm_dev = []
+        for nm in normmats:  # NaN fill with the minimum (orca_predict.py:668-671), once, on the device
+            t = torch.as_tensor(np.asarray(nm, dtype=np.float64)).to(device)
+            nan = torch.isnan(t)
+            if bool(nan.any()):
+                t = torch.where(nan, t[~nan].min(), t)
+            nm_dev.append(t)
+        per_strand, allns, starts0 = [], [], None
+        for reverse in (False, True):
+            for ii, model in enumerate(models):
+                enc4k = encode_strand(model, seq_dev, reverse)
+                enc128k = model.net1(enc4k, coarsest_only=True)[-1]
+                encs = dict(zip([32, 64, 128, 256], model.net(enc128k)))
+                preds, starts, ns = cascade_256mb(model, encs, B, nm_dev[ii], chrlen, mpos, wpos, reverse)
+                per_strand.append(preds)
+                allns.append(ns)
+                if not reverse and starts0 is None:
+                    starts0 = starts
+        n = len(models)
+        host = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])).cpu().numpy() for i in range(n)]
+        ns_host = [{lvl: torch.exp(t[0]).cpu().numpy().astype(np.float64) for lvl, t in ns.items()} for ns in allns]
+    output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
+    output["start_coords"] = [wpos - 128000000 + s * 32000 for s in starts0]
+    output["end_coords"] = [np.fmin(int(output["start_coords"][ii] + 256000000 / 2 ** ii), chrlen) for ii in range(4)]
+    output["annos"] = None
+    output["chr"] = mchr
+    output["padding_chr"] = padding_chr
+    output["normmats"] = ns_host
+    return output

@@ -1,0 +1,177 @@
+"""GPU parity: the CUDA path (through the C ABI, via the nn.Module mirrors) against the golden
+fixtures produced by the unmodified reference and against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north star): max|ours - ref| / max|ref| <= 1e-3 per output, fp32.
+The fp32 SIMT path is additionally held to 5e-5 (it differs from the reference only by fp32
+summation order and the BatchNorm fold)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+import orca_oracle as oracle
+from orca_b200 import _lib, modules, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3        # north-star tolerance
+TOL_SIMT = 5e-5   # exact-fp32 path
+
+IMPLS = ["simt", "auto"]
+
+
+def gold(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def randn(shape, seed, scale=1.0):
+    return torch.from_numpy((np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32))
+
+
+def native(module, seed):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return synthetic.init_module(module, seed).cuda()
+
+
+def tol(impl):
+    return TOL_SIMT if impl == "simt" else TOL
+
+
+@pytest.fixture(params=IMPLS)
+def impl(request):
+    _lib.set_impl(request.param)
+    yield request.param
+    _lib.set_impl("auto")
+
+
+@pytest.mark.parametrize("name", ["encoder_24k", "encoder_1mb"])
+def test_encoder_golden(name, impl):
+    g = gold(name)
+    m = native(modules.Encoder(), int(g["weight_seed"]))
+    seq = synthetic.random_sequence(1, int(g["L"]), int(g["seq_seed"]), float(g["n_fraction"]))
+    x = torch.from_numpy(seq).transpose(1, 2).cuda()  # strided view, as genomepredict passes it (orca_predict.py:334)
+    assert x.stride() == (4 * int(g["L"]), 1, 4)
+    n0 = _lib.launch_count()
+    y = m(x)
+    assert _lib.launch_count() > n0
+    assert tuple(y.shape) == g["out"].shape
+    e = relerr(y.cpu().numpy(), g["out"])
+    print(name, impl, "relerr %.2e" % e)
+    assert e <= tol(impl)
+
+
+def test_encoder_layouts_and_chunks(impl):
+    """Contiguous (B,4,L) input == channel-last view; chunked == single pass; batch handled."""
+    m = native(modules.Encoder(), 5)
+    L = 480000
+    seq = synthetic.random_sequence(2, L, 9, 0.01)
+    xt = torch.from_numpy(seq).cuda()
+    a = m(xt.transpose(1, 2))
+    b = m(xt.transpose(1, 2).contiguous())
+    assert torch.equal(a, b)
+    m.chunk_bp = 120000  # 4 chunks per sample, 112 kb halo each side
+    c = m(xt.transpose(1, 2))
+    m.chunk_bp = 0
+    assert torch.equal(a, c), "chunked encoder must be bit-identical to the single pass"
+    with torch.no_grad():
+        ref = oracle.encoder_forward(synthetic.fill_state_dict(m.state_dict(), 5), torch.from_numpy(seq).transpose(1, 2))
+    assert relerr(a.cpu().numpy(), ref.numpy()) <= tol(impl)
+    # bin sub-range (what a sequence shard computes)
+    part = m(xt.transpose(1, 2), bin_range=(30, 90))
+    assert torch.equal(part[:, :, 30:90], a[:, :, 30:90])
+
+
+@pytest.mark.parametrize("name,cls", [("encoder2_p256", modules.Encoder2), ("encoder3_p64", modules.Encoder3),
+                                      ("encoder2b_p64", modules.Encoder2b)])
+def test_unets_golden(name, cls, impl):
+    g = gold(name)
+    m = native(cls(), int(g["weight_seed"]))
+    x = randn((2, 128, int(g["P"])), int(g["x_seed"])).cuda()
+    ys = m(x)
+    for i, y in enumerate(ys):
+        assert tuple(y.shape) == g["out%d" % i].shape
+        assert relerr(y.cpu().numpy(), g["out%d" % i]) <= tol(impl), (name, i)
+    # strided (channel-last) input gives the same result
+    ys2 = m(x.transpose(1, 2).contiguous().transpose(1, 2))
+    assert all(torch.equal(a, b) for a, b in zip(ys, ys2))
+    if cls is modules.Encoder2:  # what genomepredict_256Mb consumes: net1(...)[-1]
+        last = m(x, coarsest_only=True)[-1]
+        assert torch.equal(last, ys[-1])
+
+
+@pytest.mark.parametrize("name", ["decoder_nocoarse_250", "decoder_coarse_bilinear_250", "decoder_coarse_nearest_64",
+                                  "decoder_nocoarse_nearest_30"])
+def test_decoder_golden(name, impl):
+    g = gold(name)
+    mode, S, B = str(g["mode"]), int(g["S"]), int(g["B"])
+    m = native(modules.Decoder(upsample_mode=mode), int(g["weight_seed"]))
+    mats, _ = synthetic.normmats_32mb()
+    x = randn((B, 128, S), int(g["x_seed"]), 0.5).cuda()
+    distenc = torch.log(torch.FloatTensor(mats[int(g["level"])][:S, :S][None, None]).cuda()).expand(B, -1, -1, -1)
+    yc = randn((B, 1, S // 2, S // 2), int(g["y_seed"])).cuda() if bool(g["coarse"]) else None
+    y = m(x, distenc, yc)
+    e = relerr(y.cpu().numpy(), g["out"])
+    print(name, impl, "relerr %.2e" % e)
+    assert e <= tol(impl)
+    assert torch.equal(y, y.transpose(2, 3)), "symmetrised output must be exactly symmetric"
+
+
+def test_decoder_strided_inputs(impl):
+    """x as a slice of a channel-last encoding, distenc flipped / expanded, y as a crop of a
+    previous prediction -- the views genomepredict actually passes (orca_predict.py:356-401, :703)."""
+    m = native(modules.Decoder(upsample_mode="bilinear"), 15)
+    S = 48
+    enc = randn((1, 128, 200), 1, 0.5).cuda().transpose(1, 2).contiguous().transpose(1, 2)
+    x = enc[:, :, 100:100 + S]
+    d = randn((1, 1, S, S), 2).cuda().expand(1, -1, -1, -1)
+    prev = randn((1, 1, 2 * S, 2 * S), 3).cuda()
+    yc = prev[:, :, 7:7 + S // 2, 7:7 + S // 2]
+    y = m(x, torch.flip(d, [2, 3]), yc)
+    sd = synthetic.fill_state_dict(m.state_dict(), 15)
+    with torch.no_grad():
+        ref = oracle.decoder_forward(sd, x.cpu(), torch.flip(d, [2, 3]).cpu(), yc.cpu(), "bilinear")
+    assert relerr(y.cpu().numpy(), ref.numpy()) <= tol(impl)
+
+
+@pytest.mark.parametrize("name", ["decoder1m_250", "decoder1m_40"])
+def test_decoder_1m_golden(name, impl):
+    g = gold(name)
+    m = native(modules.Decoder_1m(), int(g["weight_seed"]))
+    x = randn((int(g["B"]), 128, int(g["S"])), int(g["x_seed"]), 0.5).cuda()
+    y = m(x)
+    assert relerr(y.cpu().numpy(), g["out"]) <= tol(impl)
+
+
+def test_net_golden(impl):
+    g = gold("net_48k")
+    m = native(modules.Net(num_1d=32), int(g["weight_seed"]))
+    seq = synthetic.random_sequence(int(g["B"]), int(g["L"]), int(g["seq_seed"]), float(g["n_fraction"]))
+    pred, p1d = m(torch.from_numpy(seq).transpose(1, 2).cuda())
+    assert relerr(pred.cpu().numpy(), g["out"]) <= tol(impl)
+    assert relerr(p1d.cpu().numpy(), g["out_1d"]) <= tol(impl)
+    m2 = native(modules.Net(), 17)  # no final_1d head: returns the map only (orca_modules.py:1897-1900)
+    assert isinstance(m2(torch.from_numpy(seq).transpose(1, 2).cuda()), torch.Tensor)
+
+
+def test_background_levels():
+    import ctypes
+    g = gold("background")
+    nm = torch.from_numpy(synthetic.normmat_256mb(chrlen_bins=int(g["chrlen_bins"]))).cuda()
+    for tag, r0, level, flip in [("l256", 0, 256, False), ("l64_r", 1500, 64, True), ("l32", 4100, 32, False)]:
+        out = torch.empty((250, 250), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().orca_b200_background_forward(nm.data_ptr(), 8000, r0, level // 8, 250, int(flip),
+                                                           out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert relerr(out.cpu().numpy(), g[tag][0, 0]) <= 1e-6
+
+
+def test_errors_are_loud():
+    m = native(modules.Encoder(), 1)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 8000))  # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 4001, device="cuda"))
+    d = native(modules.Decoder(), 2)
+    with pytest.raises(RuntimeError):
+        d(torch.zeros(1, 128, 10, device="cuda"), torch.zeros(1, 1, 11, 11, device="cuda"))

@@ -1,0 +1,106 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the
+nn.Module mirrors keep the reference state_dict layout, argument validation fails loudly, and the
+synthetic generators are deterministic.  No compute entry point is called (no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from orca_b200 import _lib, models, modules, parallel, synthetic
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "orca_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(orca_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), "liborca_b200.so does not export %s" % s
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.SIGNATURES) == syms
+    assert b"sm_100a" in _lib.lib().orca_b200_version()
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    """tests/golden/state_dict_keys.json was dumped from the reference classes (make_golden.py)."""
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    ctors = {"Encoder": modules.Encoder, "Encoder2": modules.Encoder2, "Encoder2b": modules.Encoder2b,
+             "Encoder3": modules.Encoder3, "Decoder": lambda: modules.Decoder(upsample_mode="bilinear"),
+             "Decoder_1m": modules.Decoder_1m, "Net32": lambda: modules.Net(num_1d=32), "Net": modules.Net}
+    for name, ctor in ctors.items():
+        sd = ctor().state_dict()
+        got = [[k, list(v.shape)] for k, v in sd.items()]
+        assert got == want[name], name
+    assert len(want["Encoder"]) == 196 and len(want["Decoder"]) == 849
+
+
+def test_cpu_tensors_are_rejected():
+    enc = modules.Encoder()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.zeros(1, 4, 4000))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        modules.Decoder()(torch.zeros(1, 128, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(RuntimeError):
+        enc.train()
+
+
+def test_module_create_validates_architecture():
+    lib = _lib.lib()
+    handle = ctypes.c_void_p()
+    arr = (_lib.ConvParams * 3)()
+    st = lib.orca_b200_module_create(_lib.ENCODER, arr, 3, 0, 0, ctypes.byref(handle))
+    assert st == -1 and b"expects 28" in lib.orca_b200_last_error()
+    st = lib.orca_b200_module_create(99, arr, 3, 0, 0, ctypes.byref(handle))
+    assert st == -1 and b"unknown module kind" in lib.orca_b200_last_error()
+    arr = (_lib.ConvParams * 28)()
+    for p in arr:
+        p.c_in, p.c_out, p.kh, p.kw, p.dilation = 64, 64, 1, 9, 1
+    st = lib.orca_b200_module_create(_lib.ENCODER, arr, 28, 0, 0, ctypes.byref(handle))
+    assert st == -1 and b"conv 0" in lib.orca_b200_last_error()
+    assert lib.orca_b200_set_impl(7) == -1
+
+
+def test_synthetic_is_deterministic():
+    a = synthetic.fill_state_dict(modules.Encoder2b().state_dict(), 5)
+    b = synthetic.fill_state_dict(modules.Encoder2b().state_dict(), 5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    s = synthetic.random_sequence(2, 1000, 3, 0.05)
+    assert s.shape == (2, 1000, 4) and np.allclose(s.sum(-1), 1.0)
+    assert set(np.unique(s)) <= {0.0, 0.25, 1.0}
+    mats, epss = synthetic.normmats_32mb()
+    assert sorted(mats) == [1, 2, 4, 8, 16, 32] and mats[32].shape == (250, 250)
+    assert np.allclose(mats[4], mats[4].T) and epss[1] == mats[1].min()
+
+
+def test_shell_protocol():
+    sh = models.build_shell(modules, "h1esc", seed=3)
+    assert isinstance(sh, torch.nn.Module)
+    assert sorted(sh.denets) == [1, 2, 4, 8, 16, 32]
+    for attr in ("net0", "net", "denet_1_pt", "normmats", "epss"):
+        assert hasattr(sh, attr)
+    sh256 = models.build_shell(modules, "h1esc_256m", seed=3)
+    assert sorted(sh256.denets) == [32, 64, 128, 256] and hasattr(sh256, "net1")
+    assert sh256.background_cis.shape == (10000,) and np.isnan(sh256.background_cis[-1])
+    hct = models.build_shell(modules, "hctnoc", seed=3)
+    assert isinstance(hct.net, modules.Encoder2b) and not hasattr(hct, "denet_1_pt")
+    assert hct.denets[1].upsample.mode == "nearest"
+
+
+def test_shard_geometry():
+    for P, world in [(8000, 1), (8000, 2), (8000, 8), (64000, 8), (250, 4)]:
+        ranges = [parallel.shard_bins(P, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == P
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    s0, s1 = parallel.shard_window(32_000_000, 1000, 2000)
+    assert s0 == 1000 * 4000 - 116000 and s1 == 2000 * 4000 + 116000
+    assert parallel.shard_window(32_000_000, 0, 8000) == (0, 32_000_000)
