@@ -240,6 +240,9 @@ def main():
     ms_prof = timed(step_device, args.steps) / args.steps
     prof = _lib.profile_summary()
     _lib.profile_enable(False)
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "conv_profile_n%d.json" % world), "w") as f:
+            json.dump({"steps": args.steps, "ms_per_step_profiled": ms_prof, "kernels": prof}, f, indent=1)
     dom = max(prof, key=lambda r: r["ms"]) if prof else None
     roofline = None
     if dom:

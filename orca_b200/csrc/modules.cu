@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.h"
+#include "tc.h"
 
 namespace orca {
 
@@ -210,6 +211,86 @@ static int encoder_window(const ConvLayer* L, const float* x, int64_t sB, int64_
   return ORCA_B200_OK;
 }
 
+// Same program on the tcgen05 path: activations are bf16 hi/lo chunk planes (tc.h); bias/ReLU/residual
+// and the 4x / 2x max-pools are fused into the conv epilogue, the three 5x pools run as a plane kernel.
+static TcAct tc_make(void* base, int nb, int C, int64_t n) {
+  TcAct t;
+  t.nb = nb; t.C = C; t.n = n; t.npad = tc_npad(n);
+  t.hi = base;
+  t.lo = base ? static_cast<char*>(base) + tc_plane_bytes(nb, C, n) : nullptr;
+  return t;
+}
+
+static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32,
+                          int pool, int relu, cudaStream_t s) {
+  if (!g_profile.load(std::memory_order_relaxed)) return tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s);
+  ProfRec r;
+  ORCA_CUDA_OK(cudaEventCreate(&r.e0));
+  ORCA_CUDA_OK(cudaEventCreate(&r.e1));
+  ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
+  const int st = tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s);
+  ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
+  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = 1; r.tc = 1;
+  r.flop = 2.0 * (double)in.nb * (double)in.n * L.c_in * L.c_out * 9;
+  g_prof.push_back(r);
+  return st;
+}
+#define tc_conv1d tc_conv1d_prof
+
+static int encoder_window_tc(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
+                             int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
+  const size_t m = ar.mark();
+  const size_t big = 2 * tc_plane_bytes(nb, 64, n);  // stage 1 is the largest tensor of every stage
+  void* X[3] = {ar.raw(big), ar.raw(big), ar.raw(big)};
+  void* Pb = ar.raw(2 * tc_plane_bytes(nb, 64, n / 4));
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    int64_t len = n;
+    TcAct in;  // input of the stage (pooled output of the previous one)
+    for (int k = 0; k < 7; ++k) {
+      const ConvLayer* Lk = L + 4 * k;
+      const int C = Lk[0].c_out;
+      TcAct t0 = tc_make(X[0], nb, C, len), t1 = tc_make(X[1], nb, C, len), t2 = tc_make(X[2], nb, C, len);
+      if (k == 0) {
+        ORCA_TRY(tc_conv_first(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, &t0, s));
+      } else {
+        ORCA_TRY(tc_conv1d(Lk[0], in, nullptr, &t0, nullptr, 1, 0, s));
+      }
+      ORCA_TRY(tc_conv1d(Lk[1], t0, nullptr, &t1, nullptr, 1, 0, s));  // lout_k
+      ORCA_TRY(tc_conv1d(Lk[2], t1, nullptr, &t0, nullptr, 1, 1, s));
+      if (k == 6) {  // out7 only, fp32 channel-last (orca_modules.py:949-950)
+        ORCA_TRY(tc_conv1d(Lk[3], t0, nullptr, nullptr, out7, 1, 1, s));
+        break;
+      }
+      const int p = kPool[k + 1];
+      TcAct nxt = tc_make(Pb, nb, C, len / p);
+      if (p == 5) {
+        ORCA_TRY(tc_conv1d(Lk[3], t0, &t1, &t2, nullptr, 1, 1, s));  // out_k + lout_k
+        ORCA_TRY(tc_pool_planes(t2, &nxt, 5, s));
+      } else {
+        ORCA_TRY(tc_conv1d(Lk[3], t0, &t1, &nxt, nullptr, p, 1, s));  // pool fused into the epilogue
+      }
+      in = nxt;
+      len /= p;
+    }
+  }
+  ar.release(m);
+  return ORCA_B200_OK;
+}
+
+static bool use_tc_encoder(const ConvLayer* L) {
+  if (g_impl.load(std::memory_order_relaxed) == ORCA_B200_IMPL_SIMT) return false;
+  for (int i = 1; i < 28; ++i)
+    if (!L[i].tc_w) return false;
+  return true;
+}
+
+static int encoder_window_any(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
+                              int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
+  if (use_tc_encoder(L)) return encoder_window_tc(L, x, sB, sC, sL, nb, Ltot, l_begin, n, out7, ar, s);
+  return encoder_window(L, x, sB, sC, sL, nb, Ltot, l_begin, n, out7, ar, s);
+}
+
 static const int64_t kBin = 4000, kHaloBins = 28;  // x_padding = 112000, orca_modules.py:931-932
 static const int64_t kDefaultChunkBp = 4000000;
 
@@ -235,7 +316,7 @@ static int encoder_run(const orca_b200_module* m, const float* x, int64_t B, int
       const size_t mk = ar.mark();
       float* o7 = ar.f32((size_t)nb * (he - hb) * 128);
       ARENA_OK(ar);
-      ORCA_TRY(encoder_window(m->L.data(), x + b0 * sB, sB, sC, sL, nb, L, hb * kBin, n, o7, ar, s));
+      ORCA_TRY(encoder_window_any(m->L.data(), x + b0 * sB, sB, sC, sL, nb, L, hb * kBin, n, o7, ar, s));
       if (!ar.dry) {
         ORCA_CUDA_OK(cudaMemcpy2DAsync(out + (b0 * P + cb) * 128, (size_t)P * 128 * sizeof(float),
                                        o7 + (cb - hb) * 128, (size_t)(he - hb) * 128 * sizeof(float),
@@ -437,7 +518,7 @@ static int net_run(const orca_b200_module* m, const float* x, int64_t B, int64_t
   float* o7 = ar.f32((size_t)B * S * 128);
   ARENA_OK(ar);
   for (int64_t b = 0; b < B; ++b)
-    ORCA_TRY(encoder_window(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
+    ORCA_TRY(encoder_window_any(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
   ORCA_TRY(decoder_body(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, nullptr, 0, 0, 0, nullptr, 0, 0, 0, out, ar, s));
   if (m->num_1d > 0 && out_1d) {  // final_1d (orca_modules.py:1824-1830, :1852-1853)
     float* h = ar.f32((size_t)B * S * 128);
