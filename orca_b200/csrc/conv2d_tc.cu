@@ -1,0 +1,454 @@
+// tcgen05 implicit-GEMM dilated 3x3 Conv2d for sm_100a -- the Decoder / Decoder_1m hot loop
+// (orca_modules.py:22-488, :499-800), same arithmetic and kernel skeleton as conv_tc.cu.
+//
+// Layout: a (nb, C, S, S) map is hi/lo[nb][C/8][plane_rows][8] bf16 with pixel (y, x) at row
+// y*Wp + 64 + x, Wp = S + 128: every image row carries 64 zero pixels on each side, which is the
+// horizontal zero padding for every dilation d <= 64.  Vertical padding needs no memory: a tap row that
+// falls outside the image contributes nothing, so its MMAs are skipped.
+//
+// Tile = 128 consecutive pixels of one image row (the last tile of a row is shifted left to end at S).
+// For each dy in {-d, 0, +d} the producer bulk-copies ONE run of 128 + 2d pixels per 8-channel chunk;
+// the three dx taps are descriptor start offsets (0, d, 2d rows) into that run.  Weights are staged per
+// (dy, K-block) as three [Bh;Bl] tap images and stay resident in shared memory when they fit.
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "tc.h"
+#include "tc_device.cuh"
+
+namespace orca {
+
+namespace {
+using namespace tcdev;
+
+constexpr int kPX = 64;  // zero pixels on each side of an image row
+
+struct Tc2dKArgs {
+  const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;
+  const uint8_t* w;
+  const float* bias;
+  const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  long long plane_rows;
+  int nb, S, Wp, d, relu, c_in;
+  int tiles_per_row, total_tiles;
+  int NA, NW, resident;            // ring sizes
+  int a_slot_bytes, w_stage_bytes; // per-slot strides in shared memory
+};
+
+template <int C_OUT>
+__global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int NA = a.NA, NW = a.NW;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + (size_t)NA * a.a_slot_bytes;
+  float* sBias = reinterpret_cast<float*>(sW + (size_t)NW * a.w_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C_OUT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NW + 4);
+  const uint32_t bA_full = smem_u32(bars), bA_empty = bA_full + 8 * NA;
+  const uint32_t bW_full = bA_empty + 8 * NA, bW_empty = bW_full + 8 * NW;
+  const uint32_t bAcc_full = bW_empty + 8 * NW, bAcc_empty = bAcc_full + 16;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (a.c_in + 63) / 64;
+  const int R = 128 + 2 * a.d;                 // rows of one A run
+  const int kc_all = (a.c_in < 64 ? a.c_in : 64) / 8;  // chunks per K-block (32 -> 4, 64/128 -> 8)
+  const uint32_t aLoOff = (uint32_t)kc_all * R * 16;
+  const uint32_t tapBytes = 2u * kc_all * C_OUT * 16, bLoOff = (uint32_t)kc_all * C_OUT * 16;
+
+  if (tid == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(bA_full + 8 * i, 1); mbar_init(bA_empty + 8 * i, 1); }
+    for (int i = 0; i < NW; ++i) { mbar_init(bW_full + 8 * i, 1); mbar_init(bW_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < C_OUT; i += 192) sBias[i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int tiles_per_img = a.S * a.tiles_per_row;
+
+  if (warp == 0) {
+    // ================= producer =================
+    if (lane == 0) {
+      uint32_t a_it = 0, w_it = 0, loaded = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+        const int y = rem / a.tiles_per_row, tx = rem - y * a.tiles_per_row;
+        int x0 = tx * 128;
+        if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
+#pragma unroll 1
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int yy = y + (dyi - 1) * a.d;
+          if (yy < 0 || yy >= a.S) continue;
+          const long long row0 = (long long)yy * a.Wp + x0 + kPX - a.d;
+#pragma unroll 1
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
+            mbar_wait(bA_empty + 8 * slot, ph ^ 1);
+            mbar_expect_tx(bA_full + 8 * slot, 2u * kc_all * R * 16);
+            const uint32_t dst = smem_u32(sA) + slot * a.a_slot_bytes;
+            for (int c = 0; c < kc_all; ++c) {
+              const long long plane = (long long)b * (a.c_in / 8) + kb * 8 + c;
+              const long long off = (plane * a.plane_rows + row0) * 8;
+              bulk_g2s(dst + c * R * 16, a.in_hi + off, R * 16, bA_full + 8 * slot);
+              bulk_g2s(dst + aLoOff + c * R * 16, a.in_lo + off, R * 16, bA_full + 8 * slot);
+            }
+            ++a_it;
+            const int sid = dyi * nkb + kb;
+            if (a.resident) {
+              if (!((loaded >> sid) & 1u)) {
+                loaded |= 1u << sid;
+                mbar_expect_tx(bW_full + 8 * sid, 3 * tapBytes);
+                bulk_g2s(smem_u32(sW) + sid * a.w_stage_bytes, a.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, bW_full + 8 * sid);
+              }
+            } else {
+              const uint32_t ws = w_it % NW, wph = (w_it / NW) & 1;
+              mbar_wait(bW_empty + 8 * ws, wph ^ 1);
+              mbar_expect_tx(bW_full + 8 * ws, 3 * tapBytes);
+              bulk_g2s(smem_u32(sW) + ws * a.w_stage_bytes, a.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, bW_full + 8 * ws);
+              ++w_it;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(C_OUT);
+      uint32_t a_it = 0, w_it = 0, acc_it = 0, waited = 0;
+      const int ksteps = kc_all / 2;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int rem = tile % tiles_per_img;
+        const int y = rem / a.tiles_per_row;
+        const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + as * 64;
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int yy = y + (dyi - 1) * a.d;
+          if (yy < 0 || yy >= a.S) continue;
+#pragma unroll 1
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t slot = a_it % NA;
+            mbar_wait(bA_full + 8 * slot, (a_it / NA) & 1);
+            const int sid = dyi * nkb + kb;
+            uint32_t ws;
+            if (a.resident) {
+              ws = sid;
+              if (!((waited >> sid) & 1u)) { waited |= 1u << sid; mbar_wait(bW_full + 8 * ws, 0); }
+            } else {
+              ws = w_it % NW;
+              mbar_wait(bW_full + 8 * ws, (w_it / NW) & 1);
+            }
+            tc_fence_after();
+            const uint32_t aBase = smem_u32(sA) + slot * a.a_slot_bytes;
+            const uint32_t wBase = smem_u32(sW) + ws * a.w_stage_bytes;
+#pragma unroll 1
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t aoff = (2 * ks) * R * 16 + dxi * a.d * 16;
+                const uint32_t boff = dxi * tapBytes + (2 * ks) * C_OUT * 16;
+                const uint64_t ah = umma_desc(aBase + aoff, R * 16), al = umma_desc(aBase + aLoOff + aoff, R * 16);
+                const uint64_t bh = umma_desc(wBase + boff, C_OUT * 16), bl = umma_desc(wBase + bLoOff + boff, C_OUT * 16);
+                umma_bf16(d_tmem, ah, bh, idesc, accum);
+                umma_bf16(d_tmem, al, bh, idesc, 1u);
+                umma_bf16(d_tmem, ah, bl, idesc, 1u);
+                accum = 1u;
+              }
+            }
+            if (!a.resident) { umma_commit(bW_empty + 8 * ws); ++w_it; }
+            umma_commit(bA_empty + 8 * slot);
+            ++a_it;
+          }
+        }
+        umma_commit(bAcc_full + 8 * as);
+        ++acc_it;
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int y = rem / a.tiles_per_row, tx = rem - y * a.tiles_per_row;
+      int x0 = tx * 128;
+      if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(bAcc_full + 8 * as, aph);
+      tc_fence_after();
+      const int x = x0 + q * 32 + lane;
+      const bool valid = x < a.S;
+      const long long r = (long long)y * a.Wp + kPX + x;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 64 + c0, raw);
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = __uint_as_float(raw[j]) + sBias[c0 + j];
+            v[j] = a.relu ? fmaxf(t, 0.f) : t;
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const long long off = (((long long)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.plane_rows + r) * 8;
+            if (a.res_hi) add_hilo8(v + 8 * ch, a.res_hi + off, a.res_lo + off);
+            split_store8(v + 8 * ch, a.out_hi + off, a.out_lo + off);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bAcc_empty + 8 * as);
+      ++acc_it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// ---- glue on map planes -----------------------------------------------------------------------------
+// outer-sum lift straight into planes: mat[b][c][i][j] = x[b][i][c] + x[b][j][c]  (orca_modules.py:462, :783)
+__global__ void outer_sum_planes_kernel(const float* __restrict__ xcl /*[B][S][C]*/, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, int S, int C, int Wp, long long plane_rows,
+                                        long long total) {
+  const int C8 = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    long long t = i / S;
+    const int y = (int)(t % S);
+    t /= S;
+    const int ch = (int)(t % C8);
+    const long long b = t / C8;
+    const float4* pi = reinterpret_cast<const float4*>(xcl + (b * S + y) * C + ch * 8);
+    const float4* pj = reinterpret_cast<const float4*>(xcl + (b * S + x) * C + ch * 8);
+    const float4 a0 = __ldg(pi), a1 = __ldg(pi + 1), b0 = __ldg(pj), b1 = __ldg(pj + 1);
+    const float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+    const long long off = ((b * C8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
+    split_store8(v, hi + off, lo + off);
+  }
+}
+
+// single-channel 3x3 conv (distance encoding / upsampled coarse map) -> 64-channel planes; see glue.cu
+__device__ __forceinline__ float extra_src2(const float* sb, long long sH, long long sW, int S, int mode, int yy, int xx) {
+  if (yy < 0 || yy >= S || xx < 0 || xx >= S) return 0.f;
+  if (mode == 0) return __ldg(sb + yy * sH + xx * sW);
+  if (mode == 1) return __ldg(sb + (yy >> 1) * sH + (xx >> 1) * sW);
+  const int n = S >> 1;
+  const float fy = fmaxf((yy + 0.5f) * 0.5f - 0.5f, 0.f), fx = fmaxf((xx + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, n - 1), x1 = min(x0 + 1, n - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float v00 = __ldg(sb + y0 * sH + x0 * sW), v01 = __ldg(sb + y0 * sH + x1 * sW);
+  const float v10 = __ldg(sb + y1 * sH + x0 * sW), v11 = __ldg(sb + y1 * sH + x1 * sW);
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
+__global__ void extra_conv_planes_kernel(const float* __restrict__ src, long long sB, long long sH, long long sW,
+                                         const float* __restrict__ w /*[9][64]*/, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int S, int Wp, long long plane_rows, int mode,
+                                         long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    long long t = i / S;
+    const int y = (int)(t % S);
+    t /= S;
+    const int ch = (int)(t % 8);
+    const long long b = t / 8;
+    const float* sb = src + b * sB;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const float v = extra_src2(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + tp * 64 + ch * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + tp * 64 + ch * 8 + 4));
+      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+    const long long off = ((b * 8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
+    split_store8(acc, hi + off, lo + off);
+  }
+}
+
+// output head on planes: 1x1 64->5 (+BN) ReLU, 1x1 5->1  (orca_modules.py:423-428); one thread per pixel
+__global__ void final_head_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                         const float* __restrict__ w0 /*[64][5]*/, const float* __restrict__ b0,
+                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                         float* __restrict__ tmp, int S, int Wp, long long plane_rows, long long total) {
+  __shared__ float sw[64 * 5 + 16];
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) sw[i] = w0[i];
+  if (threadIdx.x < 5) { sw[320 + threadIdx.x] = b0[threadIdx.x]; sw[325 + threadIdx.x] = w1[threadIdx.x]; }
+  if (threadIdx.x == 0) sw[330] = b1[0];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    const long long t = i / S;
+    const int y = (int)(t % S);
+    const long long b = t / S;
+    float h[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long off = ((b * 8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
+      add_hilo8(v, hi + off, lo + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) h[k] = fmaf(v[j], sw[(ch * 8 + j) * 5 + k], h[k]);
+    }
+    float r = sw[330];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r = fmaf(fmaxf(h[k] + sw[320 + k], 0.f), sw[325 + k], r);
+    tmp[i] = r;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+static inline uint16_t bf16_bits_rn2(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_f32_2(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+bool tc_layer2d_eligible(const ConvLayer& L) {
+  return L.kh == 3 && L.kw == 3 && (L.c_in == 32 || L.c_in == 64 || L.c_in == 128) && (L.c_out == 32 || L.c_out == 64) &&
+         L.dil >= 1 && L.dil <= 64;
+}
+
+// Stage images in consumption order: for dy, for K-block: three dx taps, each [Bh][Bl] = [k-chunk][c_out][8] bf16.
+int tc_pack_layer2d(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::vector<void*>& allocs) {
+  if (!tc_layer2d_eligible(L)) return ORCA_B200_OK;
+  const int nkb = (L.c_in + 63) / 64, ks = L.c_in < 64 ? L.c_in : 64;
+  std::vector<uint16_t> img;
+  img.reserve((size_t)9 * L.c_in * L.c_out * 2);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int dx = 0; dx < 3; ++dx)
+        for (int part = 0; part < 2; ++part)
+          for (int c = 0; c < ks / 8; ++c)
+            for (int n = 0; n < L.c_out; ++n)
+              for (int j = 0; j < 8; ++j) {
+                const int ci = kb * 64 + c * 8 + j, tap = dy * 3 + dx;
+                const float v = w[((size_t)tap * L.c_in + ci) * L.c_out + n];
+                const uint16_t h = bf16_bits_rn2(v);
+                img.push_back(part == 0 ? h : bf16_bits_rn2(v - bf16_to_f32_2(h)));
+              }
+  void* d = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&d, img.size() * 2));
+  allocs.push_back(d);
+  ORCA_CUDA_OK(cudaMemcpy(d, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  L.tc_w = d;
+  L.tc_w_bytes = img.size() * 2;
+  return ORCA_B200_OK;
+}
+
+static int sm_count2() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s) {
+  if (!L.tc_w || !tc_layer2d_eligible(L)) { set_error("tc_conv2d: layer %d->%d has no tensor-core weights", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
+  if (in.C != L.c_in || out->C != L.c_out || out->S != in.S || out->nb != in.nb || (res && (res->C != L.c_out || res->S != in.S))) {
+    set_error("tc_conv2d: geometry mismatch");
+    return ORCA_B200_EINVAL;
+  }
+  Tc2dKArgs a;
+  a.in_hi = static_cast<const __nv_bfloat16*>(in.hi); a.in_lo = static_cast<const __nv_bfloat16*>(in.lo);
+  a.w = static_cast<const uint8_t*>(L.tc_w); a.bias = L.b;
+  a.res_hi = res ? static_cast<const __nv_bfloat16*>(res->hi) : nullptr;
+  a.res_lo = res ? static_cast<const __nv_bfloat16*>(res->lo) : nullptr;
+  a.out_hi = static_cast<__nv_bfloat16*>(out->hi); a.out_lo = static_cast<__nv_bfloat16*>(out->lo);
+  a.plane_rows = in.plane_rows; a.nb = in.nb; a.S = in.S; a.Wp = in.Wp; a.d = L.dil; a.relu = relu; a.c_in = L.c_in;
+  a.tiles_per_row = (in.S + 127) / 128; a.total_tiles = in.nb * in.S * a.tiles_per_row;
+  const int nkb = (L.c_in + 63) / 64, kc = (L.c_in < 64 ? L.c_in : 64) / 8, R = 128 + 2 * L.dil;
+  a.a_slot_bytes = 2 * kc * R * 16;
+  a.w_stage_bytes = 3 * 2 * kc * L.c_out * 16;
+  const int n_stages = 3 * nkb;
+  const int limit = 227 * 1024 - 2048;
+  if (n_stages * a.w_stage_bytes + 2 * a.a_slot_bytes <= limit) {
+    a.resident = 1; a.NW = n_stages;
+  } else {
+    a.resident = 0; a.NW = 2;
+    if (2 * a.w_stage_bytes + a.a_slot_bytes > limit) a.NW = 1;
+  }
+  int na = (limit - a.NW * a.w_stage_bytes) / a.a_slot_bytes;
+  if (na < 1) { set_error("tc_conv2d: shared memory budget exceeded"); return ORCA_B200_EUNSUPPORTED; }
+  a.NA = na > 4 ? 4 : na;
+  const int smem = a.NA * a.a_slot_bytes + a.NW * a.w_stage_bytes + L.c_out * 4 + (2 * a.NA + 2 * a.NW + 4) * 8 + 16 + 128;
+  const int sms = sm_count2();
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  if (a.total_tiles <= 0) return ORCA_B200_OK;
+  static bool cfg32 = false, cfg64 = false;
+  if (L.c_out == 32) {
+    if (!cfg32) { ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg32 = true; }
+    conv2d_tc_kernel<32><<<grid, 192, smem, s>>>(a);
+  } else {
+    if (!cfg64) { ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg64 = true; }
+    conv2d_tc_kernel<64><<<grid, 192, smem, s>>>(a);
+  }
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
+static unsigned grid_for(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+int tc_outer_sum(const float* xcl, TcMap* out, cudaStream_t s) {
+  const long long total = (long long)out->nb * (out->C / 8) * out->S * out->S;
+  outer_sum_planes_kernel<<<grid_for(total), 256, 0, s>>>(xcl, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo),
+                                                          out->S, out->C, out->Wp, out->plane_rows, total);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
+int tc_extra_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra, TcMap* out, int mode, cudaStream_t s) {
+  if (out->C != 64) { set_error("tc_extra_conv: C != 64"); return ORCA_B200_EINVAL; }
+  const long long total = (long long)out->nb * 8 * out->S * out->S;
+  extra_conv_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, sB, sH, sW, w_extra, static_cast<__nv_bfloat16*>(out->hi),
+                                                           static_cast<__nv_bfloat16*>(out->lo), out->S, out->Wp, out->plane_rows, mode, total);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
+int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp, cudaStream_t s) {
+  if (in.C != 64 || f0.c_in != 64 || f0.c_out != 5 || f1.c_in != 5 || f1.c_out != 1) { set_error("tc_final_head: bad layers"); return ORCA_B200_EINVAL; }
+  const long long total = (long long)in.nb * in.S * in.S;
+  final_head_planes_kernel<<<grid_for(total), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in.hi), static_cast<const __nv_bfloat16*>(in.lo),
+                                                           f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
+}  // namespace orca

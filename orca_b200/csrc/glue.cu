@@ -245,6 +245,14 @@ __global__ void symmetrise_kernel(const float* __restrict__ tmp, float* __restri
   }
 }
 
+int symmetrise(const float* tmp, float* out, int B, int S, cudaStream_t s) {
+  if (B <= 0 || S <= 0) return ORCA_B200_OK;
+  dim3 g2((S + 31) / 32, (S + 31) / 32, B), b2(32, 8);
+  symmetrise_kernel<<<g2, b2, 0, s>>>(tmp, out, S);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
 int final_head(const float* in, const ConvLayer& f0, const ConvLayer& f1, float* tmp, float* out, int B,
                int S, cudaStream_t s) {
   if (f0.c_in != 64 || f0.c_out != 5 || f1.c_in != 5 || f1.c_out != 1) { set_error("final_head: bad layers"); return ORCA_B200_EINVAL; }

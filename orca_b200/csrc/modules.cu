@@ -497,6 +497,131 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
   return ORCA_B200_OK;
 }
 
+// ---- the same decoder programs on the tcgen05 path (activations as bf16 hi/lo map planes, tc.h) ----
+static int tc_conv2d_prof(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s) {
+  if (!g_profile.load(std::memory_order_relaxed)) return tc_conv2d(L, in, res, out, relu, s);
+  ProfRec r;
+  ORCA_CUDA_OK(cudaEventCreate(&r.e0));
+  ORCA_CUDA_OK(cudaEventCreate(&r.e1));
+  ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
+  const int st = tc_conv2d(L, in, res, out, relu, s);
+  ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
+  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = L.dil; r.tc = 1;
+  r.flop = 2.0 * (double)in.nb * in.S * in.S * L.c_in * L.c_out * 9;
+  g_prof.push_back(r);
+  return st;
+}
+
+static TcMap map_make(void* base, int nb, int C, int S) {
+  TcMap t;
+  t.nb = nb; t.C = C; t.S = S; t.Wp = S + 128; t.plane_rows = tc2d_plane_rows(S);
+  t.hi = base;
+  t.lo = base ? static_cast<char*>(base) + tc2d_plane_bytes(nb, C, S) : nullptr;
+  return t;
+}
+
+struct MapRot {
+  void* buf[3];
+  int cur = 0, nb = 0, S = 0;
+  TcMap next(int C = 64) { cur = (cur + 1) % 3; return map_make(buf[cur], nb, C, S); }
+};
+
+// cur = lm(cur) [+ cur] ; cur = m(cur) + cur   (one residual bottleneck unit)
+static int bottleneck_tc(const ConvLayer* lm, const ConvLayer* mm, TcMap& cur, bool l_residual, MapRot& rot, void* hbuf,
+                         cudaStream_t s) {
+  TcMap h = map_make(hbuf, cur.nb, lm[0].c_out, cur.S);
+  ORCA_TRY(tc_conv2d_prof(lm[0], cur, nullptr, &h, 0, s));
+  TcMap t1 = rot.next();
+  ORCA_TRY(tc_conv2d_prof(lm[1], h, l_residual ? &cur : nullptr, &t1, 0, s));
+  TcMap h2 = map_make(hbuf, cur.nb, mm[0].c_out, cur.S);
+  ORCA_TRY(tc_conv2d_prof(mm[0], t1, nullptr, &h2, 1, s));
+  TcMap t2 = rot.next();
+  ORCA_TRY(tc_conv2d_prof(mm[1], h2, &t1, &t2, 1, s));
+  cur = t2;
+  return ORCA_B200_OK;
+}
+
+static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl, int B, int S,
+                           const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y, int64_t ysB,
+                           int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+  const size_t mk = ar.mark();
+  const size_t b64 = 2 * tc2d_plane_bytes(B, 64, S);
+  void* matb = ar.raw(2 * b64);  // 128 channels
+  MapRot rot;
+  rot.nb = B; rot.S = S;
+  rot.buf[0] = ar.raw(b64); rot.buf[1] = ar.raw(b64); rot.buf[2] = ar.raw(b64);
+  void* hbuf = ar.raw(b64);
+  void* ebuf = is_1m ? nullptr : ar.raw(b64);
+  float* tmp = ar.f32((size_t)B * S * S);
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    // pad pixels of every map must be zero; the layers only ever write valid pixels
+    ORCA_CUDA_OK(cudaMemsetAsync(matb, 0, 2 * b64, s));
+    for (int i = 0; i < 3; ++i) ORCA_CUDA_OK(cudaMemsetAsync(rot.buf[i], 0, b64, s));
+    ORCA_CUDA_OK(cudaMemsetAsync(hbuf, 0, b64, s));
+    if (ebuf) ORCA_CUDA_OK(cudaMemsetAsync(ebuf, 0, b64, s));
+    TcMap mat = map_make(matb, B, 128, S);
+    ORCA_TRY(tc_outer_sum(xcl, &mat, s));
+    TcMap cur;
+    if (is_1m) {
+      cur = mat;
+      ORCA_TRY(bottleneck_tc(L + D1M_LCONV, L + D1M_CONV, cur, false, rot, hbuf, s));
+      for (int i = 1; i < 19; ++i)
+        ORCA_TRY(bottleneck_tc(L + D1M_LCONV + 2 * i, L + D1M_CONV + 2 * i, cur, true, rot, hbuf, s));
+      ORCA_TRY(tc_final_head_tmp(cur, L[D1M_FINAL], L[D1M_FINAL + 1], tmp, s));
+    } else {
+      TcMap E = map_make(ebuf, B, 64, S);
+      ORCA_TRY(tc_extra_conv(distenc, dsB, dsH, dsW, L[DEC_LCOMBD].w_extra, &E, 0, s));
+      TcMap a0 = rot.next();
+      ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMBD], mat, &E, &a0, 0, s));
+      TcMap a1 = rot.next();
+      ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMBD + 1], a0, nullptr, &a1, 0, s));
+      TcMap a2 = rot.next();
+      ORCA_TRY(tc_conv2d_prof(L[DEC_COMBD], a1, nullptr, &a2, 1, s));
+      TcMap a3 = rot.next();
+      ORCA_TRY(tc_conv2d_prof(L[DEC_COMBD + 1], a2, &a1, &a3, 1, s));
+      cur = a3;
+      if (y) {
+        const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
+        ORCA_TRY(tc_extra_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, &E, mode, s));
+        TcMap b0 = rot.next();
+        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB], cur, &E, &b0, 0, s));
+        TcMap b1 = rot.next();
+        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB + 1], b0, nullptr, &b1, 0, s));
+        TcMap b2 = rot.next();
+        ORCA_TRY(tc_conv2d_prof(L[DEC_COMB], b1, nullptr, &b2, 1, s));
+        TcMap b3 = rot.next();
+        ORCA_TRY(tc_conv2d_prof(L[DEC_COMB + 1], b2, &b1, &b3, 1, s));
+        cur = b3;
+      } else {
+        ORCA_TRY(bottleneck_tc(L + DEC_LCONV, L + DEC_CONV, cur, false, rot, hbuf, s));
+      }
+      for (int i = 1; i < 28; ++i)
+        ORCA_TRY(bottleneck_tc(L + DEC_LCONV + 2 * i, L + DEC_CONV + 2 * i, cur, true, rot, hbuf, s));
+      ORCA_TRY(tc_final_head_tmp(cur, L[DEC_FINAL], L[DEC_FINAL + 1], tmp, s));
+    }
+    ORCA_TRY(symmetrise(tmp, out, B, S, s));
+  }
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+static bool use_tc_decoder(const ConvLayer* L, bool is_1m) {
+  if (g_impl.load(std::memory_order_relaxed) == ORCA_B200_IMPL_SIMT) return false;
+  const int n = is_1m ? D1M_N : DEC_N;
+  for (int i = 0; i < n; ++i)
+    if (L[i].kh == 3 && !L[i].tc_w) return false;
+  return true;
+}
+
+static int decoder_body_any(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl, int B, int S,
+                            const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y, int64_t ysB,
+                            int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+  if (use_tc_decoder(L, is_1m))
+    return decoder_body_tc(m, L, is_1m, xcl, B, S, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar, s);
+  return decoder_body(m, L, is_1m, xcl, B, S, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar, s);
+}
+
 static int decoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t S, int64_t xsB, int64_t xsC,
                        int64_t xsL, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
                        int64_t ysB, int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
@@ -504,8 +629,8 @@ static int decoder_run(const orca_b200_module* m, const float* x, int64_t B, int
   float* xcl = ar.f32((size_t)B * S * 128);
   ARENA_OK(ar);
   if (!ar.dry) ORCA_TRY(to_channel_last(x, xsB, xsC, xsL, xcl, (int)B, 128, S, s));
-  ORCA_TRY(decoder_body(m, m->L.data(), m->kind == ORCA_B200_DECODER_1M, xcl, (int)B, (int)S, distenc, dsB, dsH,
-                        dsW, y, ysB, ysH, ysW, out, ar, s));
+  ORCA_TRY(decoder_body_any(m, m->L.data(), m->kind == ORCA_B200_DECODER_1M, xcl, (int)B, (int)S, distenc, dsB, dsH,
+                            dsW, y, ysB, ysH, ysW, out, ar, s));
   ar.release(mk);
   return ORCA_B200_OK;
 }
@@ -519,7 +644,7 @@ static int net_run(const orca_b200_module* m, const float* x, int64_t B, int64_t
   ARENA_OK(ar);
   for (int64_t b = 0; b < B; ++b)
     ORCA_TRY(encoder_window_any(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
-  ORCA_TRY(decoder_body(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, nullptr, 0, 0, 0, nullptr, 0, 0, 0, out, ar, s));
+  ORCA_TRY(decoder_body_any(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, nullptr, 0, 0, 0, nullptr, 0, 0, 0, out, ar, s));
   if (m->num_1d > 0 && out_1d) {  // final_1d (orca_modules.py:1824-1830, :1852-1853)
     float* h = ar.f32((size_t)B * S * 128);
     ARENA_OK(ar);
@@ -579,6 +704,7 @@ static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<
   ORCA_TRY(upload(bias, &L.b, allocs));
   if (odd) ORCA_TRY(upload(wx, &L.w_extra, allocs));
   ORCA_TRY(tc_pack_layer(L, w.data(), allocs));
+  ORCA_TRY(tc_pack_layer2d(L, w.data(), allocs));
   return ORCA_B200_OK;
 }
 

@@ -1,11 +1,13 @@
-// Tensor-core (tcgen05) path: chunk-plane activations and the conv entry points (conv_tc.cu).
+// Tensor-core (tcgen05) path: chunk-plane activations and the conv entry points
+// (conv_tc.cu: Conv1d k=9; conv2d_tc.cu: dilated 3x3 Conv2d).
 #pragma once
+#include <vector>
 #include "common.h"
 
 namespace orca {
 
-// (nb, C, n) activation as two bf16 planes hi/lo[nb][C/8][npad][8]; data row l lives at row l + 4,
-// rows [0,4) and [n+4, npad) are zero (they are the convolution's zero padding).
+// ---- 1D: (nb, C, n) activation as two bf16 planes hi/lo[nb][C/8][npad][8]; data row l lives at row
+// l + 4, rows [0,4) and [n+4, npad) are zero (they are the convolution's zero padding).
 struct TcAct {
   void* hi = nullptr;
   void* lo = nullptr;
@@ -17,6 +19,7 @@ inline int64_t tc_npad(int64_t n) { return ((n + 127) / 128) * 128 + 8; }
 inline size_t tc_plane_bytes(int nb, int C, int64_t n) { return (size_t)nb * (C / 8) * tc_npad(n) * 16; }  // one of hi/lo
 
 bool tc_layer_eligible(const ConvLayer& L);
+int tc_pack_layer(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
 // out = act(conv(in) + b) [+ res], optionally max-pooled by `pool` (1, 2 or 4) along n, written either
 // as chunk planes (out_planes) or as fp32 channel-last [nb][n/pool][C_out] (out_f32).
 int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32, int pool,
@@ -24,5 +27,27 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
 int tc_conv_first(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb, int64_t Ltot,
                   int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s);
 int tc_pool_planes(const TcAct& in, TcAct* out, int p, cudaStream_t s);
+
+// ---- 2D: (nb, C, S, S) map as hi/lo[nb][C/8][plane_rows][8]; pixel (y, x) at row y*Wp + 64 + x with
+// Wp = S + 128 (64 zero pixels on each side of every image row); pad pixels must stay zero.
+struct TcMap {
+  void* hi = nullptr;
+  void* lo = nullptr;
+  int nb = 0, C = 0, S = 0, Wp = 0;
+  int64_t plane_rows = 0;
+};
+inline int64_t tc2d_plane_rows(int S) { return (int64_t)S * (S + 128) + 384; }
+inline size_t tc2d_plane_bytes(int nb, int C, int S) { return (size_t)nb * (C / 8) * tc2d_plane_rows(S) * 16; }  // one of hi/lo
+
+bool tc_layer2d_eligible(const ConvLayer& L);
+int tc_pack_layer2d(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
+int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s);
+int tc_outer_sum(const float* xcl /*[nb][S][C]*/, TcMap* out, cudaStream_t s);
+int tc_extra_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra, TcMap* out, int mode,
+                  cudaStream_t s);
+int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp /*[nb][S][S]*/, cudaStream_t s);
+
+// glue.cu
+int symmetrise(const float* tmp, float* out, int B, int S, cudaStream_t s);
 
 }  // namespace orca
