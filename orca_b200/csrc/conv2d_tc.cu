@@ -76,22 +76,27 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
 
   if (warp == 0) {
     // ================= producer =================
-    if (lane == 0) {
-      uint32_t a_it = 0, w_it = 0, loaded = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-        const int y = rem / a.tiles_per_row, tx = rem - y * a.tiles_per_row;
-        int x0 = tx * 128;
-        if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
+    // warp-uniform loop; one elected lane issues the bulk copies
+    uint32_t a_it = 0, w_it = 0, loaded = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int y = rem / a.tiles_per_row, tx = rem - y * a.tiles_per_row;
+      int x0 = tx * 128;
+      if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
 #pragma unroll 1
-        for (int dyi = 0; dyi < 3; ++dyi) {
-          const int yy = y + (dyi - 1) * a.d;
-          if (yy < 0 || yy >= a.S) continue;
-          const long long row0 = (long long)yy * a.Wp + x0 + kPX - a.d;
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        const int yy = y + (dyi - 1) * a.d;
+        if (yy < 0 || yy >= a.S) continue;
+        const long long row0 = (long long)yy * a.Wp + x0 + kPX - a.d;
 #pragma unroll 1
-          for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
-            mbar_wait(bA_empty + 8 * slot, ph ^ 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
+          mbar_wait(bA_empty + 8 * slot, ph ^ 1);
+          const int sid = dyi * nkb + kb;
+          const bool need_w = a.resident ? !((loaded >> sid) & 1u) : true;
+          const uint32_t ws = a.resident ? (uint32_t)sid : w_it % NW;
+          if (!a.resident) mbar_wait(bW_empty + 8 * ws, ((w_it / NW) & 1) ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(bA_full + 8 * slot, 2u * kc_all * R * 16);
             const uint32_t dst = smem_u32(sA) + slot * a.a_slot_bytes;
             for (int c = 0; c < kc_all; ++c) {
@@ -100,80 +105,80 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
               bulk_g2s(dst + c * R * 16, a.in_hi + off, R * 16, bA_full + 8 * slot);
               bulk_g2s(dst + aLoOff + c * R * 16, a.in_lo + off, R * 16, bA_full + 8 * slot);
             }
-            ++a_it;
-            const int sid = dyi * nkb + kb;
-            if (a.resident) {
-              if (!((loaded >> sid) & 1u)) {
-                loaded |= 1u << sid;
-                mbar_expect_tx(bW_full + 8 * sid, 3 * tapBytes);
-                bulk_g2s(smem_u32(sW) + sid * a.w_stage_bytes, a.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, bW_full + 8 * sid);
-              }
-            } else {
-              const uint32_t ws = w_it % NW, wph = (w_it / NW) & 1;
-              mbar_wait(bW_empty + 8 * ws, wph ^ 1);
+            if (need_w) {
               mbar_expect_tx(bW_full + 8 * ws, 3 * tapBytes);
               bulk_g2s(smem_u32(sW) + ws * a.w_stage_bytes, a.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, bW_full + 8 * ws);
-              ++w_it;
             }
           }
+          __syncwarp();
+          ++a_it;
+          if (a.resident) loaded |= 1u << sid; else ++w_it;
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(C_OUT);
-      uint32_t a_it = 0, w_it = 0, acc_it = 0, waited = 0;
-      const int ksteps = kc_all / 2;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int rem = tile % tiles_per_img;
-        const int y = rem / a.tiles_per_row;
-        const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-        mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + as * 64;
-        uint32_t accum = 0;
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    constexpr uint32_t idesc = umma_idesc_bf16(C_OUT);
+    uint32_t a_it = 0, w_it = 0, acc_it = 0, waited = 0;
+    const int ksteps = kc_all / 2;
+    const uint32_t aStep = (uint32_t)(2 * R * 16) >> 4, aLoStep = aLoOff >> 4;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int rem = tile % tiles_per_img;
+      const int y = rem / a.tiles_per_row;
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + as * 64;
+      uint32_t accum = 0;
 #pragma unroll 1
-        for (int dyi = 0; dyi < 3; ++dyi) {
-          const int yy = y + (dyi - 1) * a.d;
-          if (yy < 0 || yy >= a.S) continue;
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        const int yy = y + (dyi - 1) * a.d;
+        if (yy < 0 || yy >= a.S) continue;
+        const bool last_dy = (dyi == 2) || (y + a.d >= a.S && dyi == 1);
 #pragma unroll 1
-          for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t slot = a_it % NA;
-            mbar_wait(bA_full + 8 * slot, (a_it / NA) & 1);
-            const int sid = dyi * nkb + kb;
-            uint32_t ws;
-            if (a.resident) {
-              ws = sid;
-              if (!((waited >> sid) & 1u)) { waited |= 1u << sid; mbar_wait(bW_full + 8 * ws, 0); }
-            } else {
-              ws = w_it % NW;
-              mbar_wait(bW_full + 8 * ws, (w_it / NW) & 1);
-            }
-            tc_fence_after();
-            const uint32_t aBase = smem_u32(sA) + slot * a.a_slot_bytes;
-            const uint32_t wBase = smem_u32(sW) + ws * a.w_stage_bytes;
-#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t slot = a_it % NA;
+          mbar_wait(bA_full + 8 * slot, (a_it / NA) & 1);
+          const int sid = dyi * nkb + kb;
+          uint32_t ws;
+          if (a.resident) {
+            ws = sid;
+            if (!((waited >> sid) & 1u)) { waited |= 1u << sid; mbar_wait(bW_full + 8 * ws, 0); }
+          } else {
+            ws = w_it % NW;
+            mbar_wait(bW_full + 8 * ws, (w_it / NW) & 1);
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t aLo = umma_desc_lo(smem_u32(sA) + slot * a.a_slot_bytes, R * 16);
+            const uint32_t bLo = umma_desc_lo(smem_u32(sW) + ws * a.w_stage_bytes, C_OUT * 16);
+#pragma unroll
             for (int dxi = 0; dxi < 3; ++dxi) {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t aoff = (2 * ks) * R * 16 + dxi * a.d * 16;
-                const uint32_t boff = dxi * tapBytes + (2 * ks) * C_OUT * 16;
-                const uint64_t ah = umma_desc(aBase + aoff, R * 16), al = umma_desc(aBase + aLoOff + aoff, R * 16);
-                const uint64_t bh = umma_desc(wBase + boff, C_OUT * 16), bl = umma_desc(wBase + bLoOff + boff, C_OUT * 16);
-                umma_bf16(d_tmem, ah, bh, idesc, accum);
-                umma_bf16(d_tmem, al, bh, idesc, 1u);
-                umma_bf16(d_tmem, ah, bl, idesc, 1u);
-                accum = 1u;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks < ksteps) {
+                  const uint32_t ao = aLo + ks * aStep + dxi * a.d;  // dx tap = dxi*d rows of 16 B into the run
+                  const uint32_t bo = bLo + ((dxi * tapBytes) >> 4) + ks * ((2 * C_OUT * 16) >> 4);
+                  const uint64_t ah = umma_desc64(ao), al = umma_desc64(ao + aLoStep);
+                  const uint64_t bh = umma_desc64(bo), bl = umma_desc64(bo + (bLoOff >> 4));
+                  umma_bf16(d_tmem, ah, bh, idesc, accum);
+                  umma_bf16(d_tmem, al, bh, idesc, 1u);
+                  umma_bf16(d_tmem, ah, bl, idesc, 1u);
+                  accum = 1u;
+                }
               }
             }
-            if (!a.resident) { umma_commit(bW_empty + 8 * ws); ++w_it; }
+            if (!a.resident) umma_commit(bW_empty + 8 * ws);
             umma_commit(bA_empty + 8 * slot);
-            ++a_it;
+            if (last_dy && kb == nkb - 1) umma_commit(bAcc_full + 8 * as);
           }
+          __syncwarp();
+          accum = 1u;
+          if (!a.resident) ++w_it;
+          ++a_it;
         }
-        umma_commit(bAcc_full + 8 * as);
-        ++acc_it;
       }
+      ++acc_it;
     }
   } else {
     // ================= epilogue =================

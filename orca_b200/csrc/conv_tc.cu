@@ -1,5 +1,5 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM Conv1d(k=9) for sm_100a  --  the Encoder hot loop
-// (orca_modules.py:811-950) and the 128-channel U-nets.
+// (orca_modules.py:811-950) and the 128-channel U-nets (:991-1169, :1181-1276, :1286-1406).
 //
 // Arithmetic: fp32 parity needs more than one bf16 pass, so every fp32 operand
 // is split x = hi + lo (two bf16) and D += Ah*Bh + Al*Bh + Ah*Bl accumulates in fp32 in TMEM
@@ -17,101 +17,35 @@
 //     neighbouring lanes store neighbouring rows: fully coalesced.
 //
 // Kernel: persistent, one CTA per SM, warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA
-// issuer (single thread) + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bias/ReLU/residual/
-// max-pool via warp shuffles -> bf16 hi/lo planes or fp32 channel-last).  mbarrier rings: A slots (one
-// 64-channel K-block of one tile), weight stages (one (K-block, tap) [Bh;Bl] image), 2 TMEM accumulators.
+// issuer + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> bias/ReLU/residual/max-pool via warp
+// shuffles -> bf16 hi/lo planes and/or fp32 channel-last).  Producer and issuer run their loops
+// warp-uniformly and elect one lane only for the issue instructions; UMMA descriptors are a base word
+// plus compile-time offsets (loops over taps / K steps are fully unrolled).  mbarrier rings: A slots (one
+// 64-channel K-block of one tile), weight stages (one (K-block, tap) image), 2 TMEM accumulators.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "common.h"
 #include "tc.h"
+#include "tc_device.cuh"
 
 namespace orca {
 
 namespace {
+using namespace tcdev;
 
-constexpr int kRows = 136;                 // 128 output rows + 8 halo rows per A slot
+constexpr int kRows = 136;                       // 128 output rows + 8 halo rows per A slot
 constexpr int kASlotBytes = 2 * 8 * kRows * 16;  // hi + lo images of a 64-channel K-block
 constexpr int kALoOff = 8 * kRows * 16;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14), LBO>>4 [16,30) = stride between the two 16-byte K chunks of one MMA,
-// SBO>>4 [32,46) = stride between 8-row groups, version=1 [46,48), layout_type=0 [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void split_store8(const float* v, __nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-__device__ __forceinline__ void add_hilo8(float* v, const __nv_bfloat16* hi_src, const __nv_bfloat16* lo_src) {
-  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi_src));
-  const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo_src));
-  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-    v[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
-  }
-}
 
 struct TcKArgs {
   const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;
   const uint8_t* w;
   const float* bias;
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;
+  const __nv_bfloat16* res2_hi; const __nv_bfloat16* res2_lo;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   float* out_f32;
   int nb, n, npad_in, n_out, npad_out, pool, relu;
@@ -124,6 +58,7 @@ struct TcCfg {
   static constexpr int STAGE_MAX = 2 * 8 * C_OUT * 16;  // [Bh;Bl] of a 64-channel K-block
   static constexpr int NW = C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3);
   static constexpr int NA = C_OUT == 64 ? 2 : 3;
+  static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
   static constexpr int SMEM = NA * kASlotBytes + NW * STAGE_MAX + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
   __host__ __device__ static constexpr int kb_size(int kb) { return (kb == NKB - 1) ? C_IN - 64 * (NKB - 1) : 64; }
@@ -135,11 +70,15 @@ struct TcCfg {
   }
 };
 
-template <int C_IN, int C_OUT>
+// CONCAT: the two products that share A = Ah run as ONE MMA against B = [Bh;Bl] (N = 2*C_OUT, two
+// accumulator column blocks summed in the epilogue) -- 2 MMAs and 2 A-operand reads per K step instead of 3.
+template <int C_IN, int C_OUT, bool CONCAT>
 __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
   using Cfg = TcCfg<C_IN, C_OUT>;
   constexpr int NKB = Cfg::NKB, NW = Cfg::NW, NA = Cfg::NA;
   constexpr bool RESIDENT = Cfg::RESIDENT;
+  constexpr uint32_t ACC_STRIDE = CONCAT ? Cfg::ACC_STRIDE_CAT : 128;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + NA * kASlotBytes;
@@ -159,93 +98,109 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < C_OUT; i += 192) sBias[i] = a.bias[i];
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     // ================= producer: bulk copies (activation K-blocks, weight stages) =================
-    if (lane == 0) {
-      uint32_t a_it = 0, w_it = 0;
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        const int b = tile / a.tiles_per_sample, t = tile - b * a.tiles_per_sample;
-        const size_t row0 = (size_t)t * 128;  // padded row of the first halo row (l0 - 4 + 4)
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-          const int kc = Cfg::kb_size(kb) / 8;
-          const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
-          mbar_wait(bA_empty + 8 * slot, ph ^ 1);
+    uint32_t a_it = 0, w_it = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      const int b = tile / a.tiles_per_sample, t = tile - b * a.tiles_per_sample;
+      const size_t row0 = (size_t)t * 128;  // padded row of the first halo row (l0 - 4 + 4)
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int kc = Cfg::kb_size(kb) / 8;
+        const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
+        mbar_wait(bA_empty + 8 * slot, ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(bA_full + 8 * slot, 2u * kc * kRows * 16);
           const uint32_t dst = smem_u32(sA) + slot * kASlotBytes;
+          const size_t plane0 = (size_t)b * (C_IN / 8) + kb * 8;
+#pragma unroll
           for (int c = 0; c < kc; ++c) {
-            const size_t plane = (size_t)b * (C_IN / 8) + kb * 8 + c;
-            const size_t off = (plane * a.npad_in + row0) * 8;
+            const size_t off = ((plane0 + c) * a.npad_in + row0) * 8;
             bulk_g2s(dst + c * kRows * 16, a.in_hi + off, kRows * 16, bA_full + 8 * slot);
             bulk_g2s(dst + kALoOff + c * kRows * 16, a.in_lo + off, kRows * 16, bA_full + 8 * slot);
           }
-          ++a_it;
-          if (RESIDENT && ti > 0) continue;
+        }
+        __syncwarp();
+        ++a_it;
+        if (RESIDENT && ti > 0) continue;
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t ws = RESIDENT ? (uint32_t)(kb * 9 + tap) : w_it % NW, wph = (w_it / NW) & 1;
-            if (!RESIDENT) mbar_wait(bW_empty + 8 * ws, wph ^ 1);
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t ws = RESIDENT ? (uint32_t)(kb * 9 + tap) : w_it % NW, wph = (w_it / NW) & 1;
+          if (!RESIDENT) mbar_wait(bW_empty + 8 * ws, wph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(bW_full + 8 * ws, Cfg::stage_bytes(kb));
             bulk_g2s(smem_u32(sW) + ws * Cfg::STAGE_MAX, a.w + Cfg::stage_offset(kb, tap), Cfg::stage_bytes(kb),
                      bW_full + 8 * ws);
-            ++w_it;
           }
+          __syncwarp();
+          ++w_it;
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C_OUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t a_it = 0, w_it = 0, acc_it = 0;
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-        mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem + as * 128;
-        uint32_t accum = 0;
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-          const int ksteps = Cfg::kb_size(kb) / 16;
-          const uint32_t slot = a_it % NA;
-          mbar_wait(bA_full + 8 * slot, (a_it / NA) & 1);
-          const uint32_t aBase = smem_u32(sA) + slot * kASlotBytes;
-          const uint32_t bLoOff = (Cfg::kb_size(kb) / 8) * C_OUT * 16;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t ws = RESIDENT ? (uint32_t)(kb * 9 + tap) : w_it % NW;
-            if (!RESIDENT || ti == 0) mbar_wait(bW_full + 8 * ws, RESIDENT ? 0u : ((w_it / NW) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t bBase = smem_u32(sW) + ws * Cfg::STAGE_MAX;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t aoff = (2 * ks) * kRows * 16 + tap * 16, boff = (2 * ks) * C_OUT * 16;
-              const uint64_t ah = umma_desc(aBase + aoff, kRows * 16), al = umma_desc(aBase + kALoOff + aoff, kRows * 16);
-              const uint64_t bh = umma_desc(bBase + boff, C_OUT * 16), bl = umma_desc(bBase + bLoOff + boff, C_OUT * 16);
-              umma_bf16(d_tmem, ah, bh, idesc, accum);
-              umma_bf16(d_tmem, al, bh, idesc, 1u);
-              umma_bf16(d_tmem, ah, bl, idesc, 1u);
-              accum = 1u;
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    constexpr uint32_t idesc = umma_idesc_bf16(C_OUT), idesc_cat = umma_idesc_bf16(2 * C_OUT);
+    constexpr uint32_t bLbo = 2 * C_OUT * 16;  // chunk image = [Bh rows][Bl rows]
+    uint32_t a_it = 0, w_it = 0, acc_it = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + as * ACC_STRIDE;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int ksteps = Cfg::kb_size(kb) / 16;
+        const uint32_t slot = a_it % NA;
+        mbar_wait(bA_full + 8 * slot, (a_it / NA) & 1);
+        const uint32_t aLo = umma_desc_lo(smem_u32(sA) + slot * kASlotBytes, kRows * 16);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t ws = RESIDENT ? (uint32_t)(kb * 9 + tap) : w_it % NW;
+          if (!RESIDENT || ti == 0) mbar_wait(bW_full + 8 * ws, RESIDENT ? 0u : ((w_it / NW) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bLo = umma_desc_lo(smem_u32(sW) + ws * Cfg::STAGE_MAX, bLbo);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint32_t ao = aLo + ks * ((2 * kRows * 16) >> 4) + tap;  // + tap rows of 16 B
+                const uint64_t ah = umma_desc64(ao), al = umma_desc64(ao + (kALoOff >> 4));
+                const uint64_t bh = umma_desc64(bLo + ks * ((2 * bLbo) >> 4));
+                const uint32_t accum = (kb | tap | ks) != 0 ? 1u : 0u;
+                if (CONCAT) {
+                  umma_bf16(d_tmem, ah, bh, idesc_cat, accum);  // [Ah*Bh | Ah*Bl]
+                  umma_bf16(d_tmem, al, bh, idesc, 1u);         // += Al*Bh into the first block
+                } else {
+                  const uint64_t bl = umma_desc64(bLo + ks * ((2 * bLbo) >> 4) + ((C_OUT * 16) >> 4));
+                  umma_bf16(d_tmem, ah, bh, idesc, accum);
+                  umma_bf16(d_tmem, al, bh, idesc, 1u);
+                  umma_bf16(d_tmem, ah, bl, idesc, 1u);
+                }
+              }
             }
             if (!RESIDENT) umma_commit(bW_empty + 8 * ws);
-            ++w_it;
+            if (tap == 8) {
+              umma_commit(bA_empty + 8 * slot);
+              if (kb == NKB - 1) umma_commit(bAcc_full + 8 * as);
+            }
           }
-          umma_commit(bA_empty + 8 * slot);
-          ++a_it;
+          __syncwarp();
+          ++w_it;
         }
-        umma_commit(bAcc_full + 8 * as);
-        ++acc_it;
+        ++a_it;
       }
+      ++acc_it;
     }
   } else {
     // ================= epilogue warps (TMEM lane quarter = warp % 4) =================
@@ -267,18 +222,25 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
       const int b = tile / a.tiles_per_sample, t = tile - b * a.tiles_per_sample;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(bAcc_full + 8 * as, aph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_fence_after();
       const int l = t * 128 + q * 32 + lane;  // position within the sample
       const bool valid = l < a.n;
       const size_t r_in = (size_t)l + 4;
 #pragma unroll 1
       for (int c0 = 0; c0 < C_OUT; c0 += 32) {
         uint32_t raw[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
         float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + c0, raw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (CONCAT) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + C_OUT + c0, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(raw[j]) + sBias[c0 + j];
+          const float x = v[j] + sBias[c0 + j];
           v[j] = a.relu ? fmaxf(x, 0.f) : x;
         }
         if (a.res_hi && valid) {
@@ -286,6 +248,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
           for (int ch = 0; ch < 4; ++ch) {
             const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_in + r_in) * 8;
             add_hilo8(v + 8 * ch, a.res_hi + off, a.res_lo + off);
+            if (a.res2_hi) add_hilo8(v + 8 * ch, a.res2_hi + off, a.res2_lo + off);
           }
         }
         if (a.pool > 1) {
@@ -301,7 +264,8 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
             float4* dst = reinterpret_cast<float4*>(a.out_f32 + ((size_t)b * a.n_out + lo_row) * C_OUT + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+          }
+          if (a.out_hi) {
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_out + lo_row + 4) * 8;
@@ -310,28 +274,45 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_fence_before();
       mbar_arrive(bAcc_empty + 8 * as);
       ++acc_it;
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+template <int C_IN, int C_OUT, bool CONCAT>
+int launch_tc_impl(const TcKArgs& a, int sms, cudaStream_t s) {
+  using Cfg = TcCfg<C_IN, C_OUT>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    ORCA_CUDA_OK(cudaFuncSetAttribute(conv1d_tc_kernel<C_IN, C_OUT, CONCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  conv1d_tc_kernel<C_IN, C_OUT, CONCAT><<<grid, 192, Cfg::SMEM, s>>>(a);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
+// bit i of the mask selects CONCAT for C_OUT = 64 (bit 0), 96 (bit 1), 128 (bit 2); env ORCA_B200_TC_CONCAT
+int concat_mask() {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("ORCA_B200_TC_CONCAT");
+    mask = e ? atoi(e) : 7;
+  }
+  return mask;
 }
 
 template <int C_IN, int C_OUT>
 int launch_tc(const TcKArgs& a, int sms, cudaStream_t s) {
-  using Cfg = TcCfg<C_IN, C_OUT>;
-  static bool configured = false;  // per (C_IN, C_OUT) instantiation
-  if (!configured) {
-    ORCA_CUDA_OK(cudaFuncSetAttribute(conv1d_tc_kernel<C_IN, C_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    configured = true;
-  }
-  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv1d_tc_kernel<C_IN, C_OUT><<<grid, 192, Cfg::SMEM, s>>>(a);
-  ORCA_LAUNCH_OK();
-  return ORCA_B200_OK;
+  const int bit = C_OUT == 64 ? 1 : (C_OUT == 96 ? 2 : 4);
+  if (concat_mask() & bit) return launch_tc_impl<C_IN, C_OUT, true>(a, sms, s);
+  return launch_tc_impl<C_IN, C_OUT, false>(a, sms, s);
 }
 
 // ---- first layer (4 -> 64) writing chunk planes; pool-5 on planes ---------------------------------
@@ -471,7 +452,8 @@ bool tc_layer_eligible(const ConvLayer& L) {
          (L.c_out == 64 || L.c_out == 96 || L.c_out == 128) && L.c_out >= L.c_in;
 }
 
-// Stage images in consumption order: for K-block kb, for tap: [Bh][Bl], each [k-chunk][c_out][8] bf16.
+// Stage images in consumption order: for K-block kb, for tap: [k-chunk][Bh rows | Bl rows][8] bf16, i.e. one
+// K-major operand of 2*c_out rows whose first/second half are the hi/lo parts of the folded weights.
 int tc_pack_layer(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::vector<void*>& allocs) {
   if (!tc_layer_eligible(L)) return ORCA_B200_OK;
   const int nkb = (L.c_in + 63) / 64;
@@ -480,8 +462,8 @@ int tc_pack_layer(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::vect
   for (int kb = 0; kb < nkb; ++kb) {
     const int ks = (kb == nkb - 1) ? L.c_in - 64 * (nkb - 1) : 64;
     for (int tap = 0; tap < 9; ++tap)
-      for (int part = 0; part < 2; ++part)
-        for (int c = 0; c < ks / 8; ++c)
+      for (int c = 0; c < ks / 8; ++c)
+        for (int part = 0; part < 2; ++part)
           for (int n = 0; n < L.c_out; ++n)
             for (int j = 0; j < 8; ++j) {
               const int ci = kb * 64 + c * 8 + j;
@@ -505,21 +487,21 @@ int conv_tc(const ConvLayer&, const ConvCall&, cudaStream_t) {
   return ORCA_B200_EUNSUPPORTED;
 }
 
-static int g_sms = 0;
 static int sm_count() {
-  if (g_sms == 0) {
+  static int sms = 0;
+  if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms <= 0) g_sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
   }
-  return g_sms;
+  return sms;
 }
 
 int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32, int pool,
-              int relu, cudaStream_t s) {
+              int relu, cudaStream_t s, const TcAct* res2) {
   if (!L.tc_w) { set_error("tc_conv1d: layer %d->%d has no tensor-core weights", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
-  if (in.C != L.c_in || (pool != 1 && pool != 2 && pool != 4) || in.n % pool != 0 || (out_planes == nullptr) == (out_f32 == nullptr)) {
+  if (in.C != L.c_in || (pool != 1 && pool != 2 && pool != 4) || in.n % pool != 0 || (out_planes == nullptr && out_f32 == nullptr) || (res2 && !res)) {
     set_error("tc_conv1d: bad call (C=%d c_in=%d pool=%d n=%lld)", in.C, L.c_in, pool, (long long)in.n);
     return ORCA_B200_EINVAL;
   }
@@ -528,6 +510,8 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
   a.w = static_cast<const uint8_t*>(L.tc_w); a.bias = L.b;
   a.res_hi = res ? static_cast<const __nv_bfloat16*>(res->hi) : nullptr;
   a.res_lo = res ? static_cast<const __nv_bfloat16*>(res->lo) : nullptr;
+  a.res2_hi = res2 ? static_cast<const __nv_bfloat16*>(res2->hi) : nullptr;
+  a.res2_lo = res2 ? static_cast<const __nv_bfloat16*>(res2->lo) : nullptr;
   a.out_hi = out_planes ? static_cast<__nv_bfloat16*>(out_planes->hi) : nullptr;
   a.out_lo = out_planes ? static_cast<__nv_bfloat16*>(out_planes->lo) : nullptr;
   a.out_f32 = out_f32;
@@ -535,6 +519,7 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
   a.npad_out = out_planes ? (int)out_planes->npad : 0;
   a.pool = pool; a.relu = relu;
   a.tiles_per_sample = (int)((in.n + 127) / 128); a.total_tiles = a.tiles_per_sample * in.nb;
+  if (res2 && (res2->C != L.c_out || res2->n != in.n || res2->npad != in.npad || res2->nb != in.nb)) { set_error("tc_conv1d: residual-2 geometry mismatch"); return ORCA_B200_EINVAL; }
   if (res && (res->C != L.c_out || res->n != in.n || res->npad != in.npad || res->nb != in.nb)) { set_error("tc_conv1d: residual geometry mismatch"); return ORCA_B200_EINVAL; }
   if (out_planes && (out_planes->C != L.c_out || out_planes->n != in.n / pool || out_planes->nb != in.nb)) { set_error("tc_conv1d: output geometry mismatch"); return ORCA_B200_EINVAL; }
   if (a.total_tiles <= 0) return ORCA_B200_OK;

@@ -222,15 +222,15 @@ static TcAct tc_make(void* base, int nb, int C, int64_t n) {
 }
 
 static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32,
-                          int pool, int relu, cudaStream_t s) {
-  if (!g_profile.load(std::memory_order_relaxed)) return tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s);
+                          int pool, int relu, cudaStream_t s, const TcAct* res2 = nullptr) {
+  if (!g_profile.load(std::memory_order_relaxed)) return tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s, res2);
   ProfRec r;
   ORCA_CUDA_OK(cudaEventCreate(&r.e0));
   ORCA_CUDA_OK(cudaEventCreate(&r.e1));
   ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
-  const int st = tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s);
+  const int st = tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s, res2);
   ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
-  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = 1; r.tc = 1;
+  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = 0; r.tc = 1;  // dil = 0 marks Conv1d in the profile
   r.flop = 2.0 * (double)in.nb * (double)in.n * L.c_in * L.c_out * 9;
   g_prof.push_back(r);
   return st;
@@ -394,6 +394,73 @@ static int unet_run(const orca_b200_module* m, const float* x, int64_t B, int64_
   }
   ar.release(mk);
   return ORCA_B200_OK;
+}
+
+// The U-nets on the tcgen05 path: same program, activations as chunk planes; every tensor the caller
+// receives is additionally written as fp32 channel-last by the producing conv's epilogue.
+static int unet_run_tc(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
+                       int64_t sL, float* const* outs, int n_out, int coarsest_only, Arena& ar, cudaStream_t s) {
+  const int n = n_out - 1, nb = (int)B;
+  const bool has_up = m->kind != ORCA_B200_ENCODER2B;
+  const bool direct = !has_up;
+  const ConvLayer* Ll = m->L.data();
+  const ConvLayer* Lb = Ll + 2 * n;
+  const ConvLayer* Ldl = Lb + 2 * n;
+  const ConvLayer* Ldb = Ldl + 2 * n;
+  const size_t mk = ar.mark();
+  auto planes = [&](int64_t len) { return ar.raw(2 * tc_plane_bytes(nb, 128, len)); };
+  float* xcl = (direct && !coarsest_only) ? (ar.dry ? nullptr : outs[0]) : ar.f32((size_t)B * P * 128);
+  std::vector<void*> encb(n + 1);
+  for (int i = 0; i <= n; ++i) encb[i] = planes(P >> i);
+  void* T0 = planes(P);
+  void* T1 = planes(P);
+  void* Pb = planes(P);
+  void* U[2] = {planes(P), planes(P)};
+  ARENA_OK(ar);
+  if (!ar.dry) {
+    ORCA_TRY(to_channel_last(x, sB, sC, sL, xcl, nb, 128, P, s));
+    std::vector<TcAct> enc(n + 1);
+    enc[0] = tc_make(encb[0], nb, 128, P);
+    ORCA_TRY(tc_from_channel_last(xcl, &enc[0], s));
+    int64_t len = P;
+    for (int i = 0; i < n; ++i) {  // pooling half
+      TcAct pooled = tc_make(Pb, nb, 128, len / 2);
+      ORCA_TRY(tc_pool_planes(enc[i], &pooled, 2, s));
+      len >>= 1;
+      TcAct t0 = tc_make(T0, nb, 128, len), t1 = tc_make(T1, nb, 128, len);
+      enc[i + 1] = tc_make(encb[i + 1], nb, 128, len);
+      ORCA_TRY(tc_conv1d(Ll[2 * i], pooled, nullptr, &t0, nullptr, 1, 0, s));
+      ORCA_TRY(tc_conv1d(Ll[2 * i + 1], t0, nullptr, &t1, nullptr, 1, 0, s));  // lout
+      ORCA_TRY(tc_conv1d(Lb[2 * i], t1, nullptr, &t0, nullptr, 1, 1, s));
+      const bool to_out = (i + 1 == n) || (direct && !coarsest_only);
+      ORCA_TRY(tc_conv1d(Lb[2 * i + 1], t0, &t1, &enc[i + 1], to_out ? outs[i + 1] : nullptr, 1, 1, s));
+    }
+    if (has_up && !coarsest_only) {
+      TcAct cur = enc[n];
+      for (int j = 0; j < n; ++j) {  // upsampling half, skip connections in reverse
+        const int lvl = n - 1 - j;
+        TcAct up = tc_make(Pb, nb, 128, len * 2);
+        ORCA_TRY(tc_upsample2_planes(cur, &up, s));
+        len <<= 1;
+        TcAct t0 = tc_make(T0, nb, 128, len), t1 = tc_make(T1, nb, 128, len), u = tc_make(U[j & 1], nb, 128, len);
+        ORCA_TRY(tc_conv1d(Ldl[2 * j], up, nullptr, &t0, nullptr, 1, 0, s));
+        ORCA_TRY(tc_conv1d(Ldl[2 * j + 1], t0, nullptr, &t1, nullptr, 1, 0, s));  // lout
+        ORCA_TRY(tc_conv1d(Ldb[2 * j], t1, nullptr, &t0, nullptr, 1, 1, s));
+        ORCA_TRY(tc_conv1d(Ldb[2 * j + 1], t0, &t1, &u, outs[lvl], 1, 1, s, &enc[lvl]));  // conv + lout + skip
+        cur = u;
+      }
+    }
+  }
+  ar.release(mk);
+  return ORCA_B200_OK;
+}
+
+static int unet_run_any(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
+                        int64_t sL, float* const* outs, int n_out, int coarsest_only, Arena& ar, cudaStream_t s) {
+  bool tc = g_impl.load(std::memory_order_relaxed) != ORCA_B200_IMPL_SIMT;
+  for (const ConvLayer& l : m->L) tc = tc && l.tc_w;
+  if (tc) return unet_run_tc(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, s);
+  return unet_run(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -851,10 +918,10 @@ size_t orca_b200_encoder2_workspace_bytes(const orca_b200_module* m, int64_t B, 
   if (unet_args_ok(m, B, P, n_out) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
   // worst case = coarsest_only (nothing lands in caller buffers)
-  unet_run(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 1, ar, nullptr);
+  unet_run_any(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 1, ar, nullptr);
   size_t a = ar.peak;
   Arena ar2; ar2.dry = true;
-  unet_run(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 0, ar2, nullptr);
+  unet_run_any(m, nullptr, B, P, 0, 0, 0, nullptr, n_out, 0, ar2, nullptr);
   return (a > ar2.peak ? a : ar2.peak) + 256;
 }
 
@@ -868,7 +935,7 @@ int orca_b200_encoder2_forward(const orca_b200_module* m, const float* x, int64_
   for (int i = 0; i < n_out; ++i)
     if (!coarsest_only || i == n_out - 1) ORCA_TRY(check_ptr_device(outs[i], "encoder2: outs[i]"));
   Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
-  return unet_run(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, static_cast<cudaStream_t>(stream));
+  return unet_run_any(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, static_cast<cudaStream_t>(stream));
 }
 
 // ---- Decoder / Decoder_1m ----------------------------------------------------------------------

@@ -22,8 +22,12 @@ bool tc_layer_eligible(const ConvLayer& L);
 int tc_pack_layer(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
 // out = act(conv(in) + b) [+ res], optionally max-pooled by `pool` (1, 2 or 4) along n, written either
 // as chunk planes (out_planes) or as fp32 channel-last [nb][n/pool][C_out] (out_f32).
+// Both outputs may be requested at once; res2 is a second residual with the geometry of res.
 int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32, int pool,
-              int relu, cudaStream_t s);
+              int relu, cudaStream_t s, const TcAct* res2 = nullptr);
+// nearest x2 upsample / channel-last fp32 -> planes, on chunk planes (U-net glue)
+int tc_upsample2_planes(const TcAct& in, TcAct* out, cudaStream_t s);
+int tc_from_channel_last(const float* xcl /*[nb][n][C]*/, TcAct* out, cudaStream_t s);
 int tc_conv_first(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb, int64_t Ltot,
                   int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s);
 int tc_pool_planes(const TcAct& in, TcAct* out, int p, cudaStream_t s);

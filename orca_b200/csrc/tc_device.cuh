@@ -89,3 +89,27 @@ __device__ __forceinline__ void add_hilo8(float* v, const __nv_bfloat16* hi_src,
 
 }  // namespace tcdev
 }  // namespace orca
+
+namespace orca {
+namespace tcdev {
+// One elected lane of a fully-converged warp (the CUTLASS elect_one_sync idiom).  Role loops run
+// warp-uniformly and only the issue instructions sit under this predicate, so ptxas keeps descriptors in
+// uniform registers instead of wrapping every UTCHMMA / UBLKCP in a VOTEU/ELECT/BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: hi word is constant (SBO = 128 B, version 1); lo word = start>>4 | (LBO>>4)<<16,
+// so advancing the start address by `bytes` is lo += bytes >> 4.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+constexpr uint32_t kUmmaDescHi = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t lo) { return ((uint64_t)kUmmaDescHi << 32) | lo; }
+}  // namespace tcdev
+}  // namespace orca
