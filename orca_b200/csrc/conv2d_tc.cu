@@ -37,7 +37,27 @@ struct Tc2dKArgs {
   int a_slot_bytes, w_stage_bytes; // per-slot strides in shared memory
 };
 
-template <int C_OUT>
+// All MMAs of one (dy, K-block) stage: 3 dx taps x KSTEPS K steps x {Ah x [Bh;Bl] (N = 2*C_OUT), Al x Bh}.
+// FIRST0: the very first MMA of the tile overwrites the accumulator.
+template <int C_OUT, int KSTEPS, bool FIRST>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t aLo, uint32_t bLo, uint32_t aStep, uint32_t aLoStep,
+                                            uint32_t tapStep, uint32_t d, bool first_kb) {
+  constexpr uint32_t idesc = umma_idesc_bf16(C_OUT), idesc_cat = umma_idesc_bf16(2 * C_OUT);
+  constexpr uint32_t bStep = (2u * 2 * C_OUT * 16) >> 4;
+#pragma unroll
+  for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint32_t ao = aLo + ks * aStep + dxi * d;  // dx tap = dxi*d rows of 16 B into the run
+      const uint32_t bo = bLo + dxi * tapStep + ks * bStep;
+      const uint32_t accum = (FIRST && dxi == 0 && ks == 0) ? (first_kb ? 0u : 1u) : 1u;
+      umma_bf16(d_tmem, umma_desc64(ao), umma_desc64(bo), idesc_cat, accum);
+      umma_bf16(d_tmem, umma_desc64(ao + aLoStep), umma_desc64(bo), idesc, 1u);
+    }
+  }
+}
+
+template <int C_OUT, int KSTEPS>
 __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int NA = a.NA, NW = a.NW;
@@ -55,7 +75,7 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
   const int R = 128 + 2 * a.d;                 // rows of one A run
   const int kc_all = (a.c_in < 64 ? a.c_in : 64) / 8;  // chunks per K-block (32 -> 4, 64/128 -> 8)
   const uint32_t aLoOff = (uint32_t)kc_all * R * 16;
-  const uint32_t tapBytes = 2u * kc_all * C_OUT * 16, bLoOff = (uint32_t)kc_all * C_OUT * 16;
+  const uint32_t tapBytes = 2u * kc_all * C_OUT * 16;  // one tap image: [k-chunk][Bh rows | Bl rows][16 B]
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(bA_full + 8 * i, 1); mbar_init(bA_empty + 8 * i, 1); }
@@ -64,7 +84,7 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < C_OUT; i += 192) sBias[i] = a.bias[i];
@@ -84,7 +104,8 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
       int x0 = tx * 128;
       if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
 #pragma unroll 1
-      for (int dyi = 0; dyi < 3; ++dyi) {
+      for (int si = 0; si < 3; ++si) {
+        const int dyi = si == 0 ? 1 : (si == 1 ? 0 : 2);  // centre row first (always inside the image)
         const int yy = y + (dyi - 1) * a.d;
         if (yy < 0 || yy >= a.S) continue;
         const long long row0 = (long long)yy * a.Wp + x0 + kPX - a.d;
@@ -118,23 +139,21 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
     }
   } else if (warp == 1) {
     // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
-    constexpr uint32_t idesc = umma_idesc_bf16(C_OUT);
     uint32_t a_it = 0, w_it = 0, acc_it = 0, waited = 0;
-    const int ksteps = kc_all / 2;
-    const uint32_t aStep = (uint32_t)(2 * R * 16) >> 4, aLoStep = aLoOff >> 4;
+    const uint32_t aStep = (uint32_t)(2 * R * 16) >> 4, aLoStep = aLoOff >> 4, tapStep = tapBytes >> 4;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int rem = tile % tiles_per_img;
       const int y = rem / a.tiles_per_row;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(bAcc_empty + 8 * as, aph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem + as * 64;
-      uint32_t accum = 0;
+      const uint32_t d_tmem = tmem + as * 128;
+      const int last_dyi = (y + a.d < a.S) ? 2 : ((y - a.d >= 0) ? 0 : 1);
 #pragma unroll 1
-      for (int dyi = 0; dyi < 3; ++dyi) {
+      for (int si = 0; si < 3; ++si) {
+        const int dyi = si == 0 ? 1 : (si == 1 ? 0 : 2);  // same order as the producer
         const int yy = y + (dyi - 1) * a.d;
         if (yy < 0 || yy >= a.S) continue;
-        const bool last_dy = (dyi == 2) || (y + a.d >= a.S && dyi == 1);
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t slot = a_it % NA;
@@ -149,31 +168,17 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
             mbar_wait(bW_full + 8 * ws, (w_it / NW) & 1);
           }
           tc_fence_after();
+          // warp-uniform descriptor base words
+          const uint32_t aLo = __shfl_sync(0xffffffffu, umma_desc_lo(smem_u32(sA) + slot * a.a_slot_bytes, R * 16), 0);
+          const uint32_t bLo = __shfl_sync(0xffffffffu, umma_desc_lo(smem_u32(sW) + ws * a.w_stage_bytes, 2 * C_OUT * 16), 0);
           if (elect_one()) {
-            const uint32_t aLo = umma_desc_lo(smem_u32(sA) + slot * a.a_slot_bytes, R * 16);
-            const uint32_t bLo = umma_desc_lo(smem_u32(sW) + ws * a.w_stage_bytes, C_OUT * 16);
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks < ksteps) {
-                  const uint32_t ao = aLo + ks * aStep + dxi * a.d;  // dx tap = dxi*d rows of 16 B into the run
-                  const uint32_t bo = bLo + ((dxi * tapBytes) >> 4) + ks * ((2 * C_OUT * 16) >> 4);
-                  const uint64_t ah = umma_desc64(ao), al = umma_desc64(ao + aLoStep);
-                  const uint64_t bh = umma_desc64(bo), bl = umma_desc64(bo + (bLoOff >> 4));
-                  umma_bf16(d_tmem, ah, bh, idesc, accum);
-                  umma_bf16(d_tmem, al, bh, idesc, 1u);
-                  umma_bf16(d_tmem, ah, bl, idesc, 1u);
-                  accum = 1u;
-                }
-              }
-            }
+            if (si == 0) issue_stage<C_OUT, KSTEPS, true>(d_tmem, aLo, bLo, aStep, aLoStep, tapStep, (uint32_t)a.d, kb == 0);
+            else issue_stage<C_OUT, KSTEPS, false>(d_tmem, aLo, bLo, aStep, aLoStep, tapStep, (uint32_t)a.d, false);
             if (!a.resident) umma_commit(bW_empty + 8 * ws);
             umma_commit(bA_empty + 8 * slot);
-            if (last_dy && kb == nkb - 1) umma_commit(bAcc_full + 8 * as);
+            if (dyi == last_dyi && kb == nkb - 1) umma_commit(bAcc_full + 8 * as);
           }
           __syncwarp();
-          accum = 1u;
           if (!a.resident) ++w_it;
           ++a_it;
         }
@@ -190,26 +195,37 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
       int x0 = tx * 128;
       if (x0 + 128 > a.S) x0 = a.S > 128 ? a.S - 128 : 0;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      mbar_wait(bAcc_full + 8 * as, aph);
-      tc_fence_after();
       const int x = x0 + q * 32 + lane;
       const bool valid = x < a.S;
       const long long r = (long long)y * a.Wp + kPX + x;
-#pragma unroll 1
+      // residual fetched BEFORE waiting for the accumulator: its L2 latency overlaps the tile's MMAs
+      float res[C_OUT];
+#pragma unroll
+      for (int j = 0; j < C_OUT; ++j) res[j] = 0.f;
+      if (a.res_hi && valid) {
+#pragma unroll
+        for (int ch = 0; ch < C_OUT / 8; ++ch) {
+          const long long off = (((long long)b * (C_OUT / 8) + ch) * a.plane_rows + r) * 8;
+          add_hilo8(res + 8 * ch, a.res_hi + off, a.res_lo + off);
+        }
+      }
+      mbar_wait(bAcc_full + 8 * as, aph);
+      tc_fence_after();
+#pragma unroll
       for (int c0 = 0; c0 < C_OUT; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 64 + c0, raw);
+        uint32_t raw[32], raw2[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + C_OUT + c0, raw2);
         if (valid) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float t = __uint_as_float(raw[j]) + sBias[c0 + j];
-            v[j] = a.relu ? fmaxf(t, 0.f) : t;
+            const float t = __uint_as_float(raw[j]) + __uint_as_float(raw2[j]) + sBias[c0 + j];
+            v[j] = (a.relu ? fmaxf(t, 0.f) : t) + res[c0 + j];
           }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             const long long off = (((long long)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.plane_rows + r) * 8;
-            if (a.res_hi) add_hilo8(v + 8 * ch, a.res_hi + off, a.res_lo + off);
             split_store8(v + 8 * ch, a.out_hi + off, a.out_lo + off);
           }
         }
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // ---- glue on map planes -----------------------------------------------------------------------------
@@ -338,11 +354,11 @@ static inline float bf16_to_f32_2(uint16_t b) {
 }
 
 bool tc_layer2d_eligible(const ConvLayer& L) {
-  return L.kh == 3 && L.kw == 3 && (L.c_in == 32 || L.c_in == 64 || L.c_in == 128) && (L.c_out == 32 || L.c_out == 64) &&
+  return L.kh == 3 && L.kw == 3 && ((L.c_in == 32 && L.c_out == 64) || ((L.c_in == 64 || L.c_in == 128) && (L.c_out == 32 || L.c_out == 64))) &&
          L.dil >= 1 && L.dil <= 64;
 }
 
-// Stage images in consumption order: for dy, for K-block: three dx taps, each [Bh][Bl] = [k-chunk][c_out][8] bf16.
+// Stage images in consumption order: for dy, for K-block: three dx taps, each [k-chunk][Bh rows | Bl rows][8] bf16.
 int tc_pack_layer2d(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::vector<void*>& allocs) {
   if (!tc_layer2d_eligible(L)) return ORCA_B200_OK;
   const int nkb = (L.c_in + 63) / 64, ks = L.c_in < 64 ? L.c_in : 64;
@@ -351,8 +367,8 @@ int tc_pack_layer2d(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::ve
   for (int dy = 0; dy < 3; ++dy)
     for (int kb = 0; kb < nkb; ++kb)
       for (int dx = 0; dx < 3; ++dx)
-        for (int part = 0; part < 2; ++part)
-          for (int c = 0; c < ks / 8; ++c)
+        for (int c = 0; c < ks / 8; ++c)
+          for (int part = 0; part < 2; ++part)
             for (int n = 0; n < L.c_out; ++n)
               for (int j = 0; j < 8; ++j) {
                 const int ci = kb * 64 + c * 8 + j, tap = dy * 3 + dx;
@@ -412,14 +428,17 @@ int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out,
   const int sms = sm_count2();
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
   if (a.total_tiles <= 0) return ORCA_B200_OK;
-  static bool cfg32 = false, cfg64 = false;
-  if (L.c_out == 32) {
-    if (!cfg32) { ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg32 = true; }
-    conv2d_tc_kernel<32><<<grid, 192, smem, s>>>(a);
-  } else {
-    if (!cfg64) { ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg64 = true; }
-    conv2d_tc_kernel<64><<<grid, 192, smem, s>>>(a);
+  static bool configured = false;
+  if (!configured) {
+    ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
+  if (L.c_out == 32 && kc == 8) conv2d_tc_kernel<32, 4><<<grid, 192, smem, s>>>(a);
+  else if (L.c_out == 64 && kc == 8) conv2d_tc_kernel<64, 4><<<grid, 192, smem, s>>>(a);
+  else if (L.c_out == 64 && kc == 4) conv2d_tc_kernel<64, 2><<<grid, 192, smem, s>>>(a);
+  else { set_error("tc_conv2d: no kernel for %d->%d", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }
