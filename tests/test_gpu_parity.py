@@ -175,3 +175,66 @@ def test_errors_are_loud():
     d = native(modules.Decoder(), 2)
     with pytest.raises(RuntimeError):
         d(torch.zeros(1, 128, 10, device="cuda"), torch.zeros(1, 1, 11, 11, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole passes: the B200 drivers (orca_b200.predict / orca_b200.parallel) against fixtures produced by
+# the UNMODIFIED orca_predict.genomepredict / genomepredict_256Mb on reference-module shells
+# ---------------------------------------------------------------------------------------------------
+def test_genomepredict_32mb_golden():
+    from orca_b200 import models, parallel, predict
+    g = gold("genomepredict_32mb")
+    shell = models.H1esc(seed=int(g["shell_seed"]))
+    seq = synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"]))
+    mpos, wpos = int(g["mpos"]), int(g["wpos"])
+    out = predict.genomepredict(seq, "chrS", mpos, wpos, models=[shell])
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("genomepredict 32 Mb relerr per level (32..1 Mb):", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
+    # the bench's sharded runner is the same computation (world size 1)
+    runner = parallel.ShardedForward(shell, 32_000_000, 0, 1, torch.device("cuda"))
+    runner.upload(torch.from_numpy(seq))
+    maps = runner.forward(mpos, wpos).cpu().numpy()
+    assert max(relerr(maps[i], g["predictions"][i]) for i in range(6)) <= TOL
+
+
+def test_genomepredict_256mb_driver_golden():
+    """Driver logic of the 256 Mb path (net1(...)[-1], Encoder3, background levels on the GPU, cascade index
+    math with chrlen clipping, strand flip) with the fixture's stub 4 kb encoding in place of net0."""
+    from orca_b200 import models, predict
+    g = gold("genomepredict_256mb_stub")
+    shell = models.H1esc_256M(seed=int(g["shell_seed"]))
+
+    class StubNet0(torch.nn.Module):
+        def forward(self, x, reverse_complement=False):
+            e = np.random.default_rng(int(g["enc_seed"])).standard_normal((x.shape[0], 128, 64000)) * 0.5
+            return torch.from_numpy(e.astype(np.float32)).cuda()
+    shell.net0 = StubNet0()
+    seq = synthetic.random_sequence(1, 4000, 107)
+    nm = synthetic.normmat_256mb(chrlen_bins=int(g["chrlen_bins"]))
+    out = predict.genomepredict_256Mb(seq, "chrS", [nm], int(g["chrlen"]), int(g["mpos"]), int(g["wpos"]), models=[shell])
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("genomepredict 256 Mb (stub encoder) relerr per level (256..32 Mb):", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
+
+
+def test_encoder_locality_at_scale():
+    """Size-independent property at a size the oracle cannot reach in full: bins of an 8 Mb encode equal the
+    oracle's encode of a 1.2 Mb window around them (receptive field 104,016 bp < 112,000 bp halo), on both
+    strands (the reverse strand is read in place with negative strides)."""
+    m = native(modules.Encoder(), 6)
+    L = 8_000_000
+    seq = synthetic.random_sequence(1, L, 12)
+    xd = torch.from_numpy(seq).cuda()
+    sd = synthetic.fill_state_dict(m.state_dict(), 6)
+    for rc in (False, True):
+        full = m(xd.transpose(1, 2), reverse_complement=rc).cpu()
+        s = np.ascontiguousarray(seq[:, ::-1, ::-1]) if rc else seq
+        for b0 in (0, 977, 1990):  # first, interior (chunk boundary at bin 1000), last
+            lo, hi = max(b0 * 4000 - 112000, 0), min((b0 + 10) * 4000 + 112000, L)
+            with torch.no_grad():
+                ref = oracle.encoder_run(sd, torch.from_numpy(s[:, lo:hi]).transpose(1, 2))
+            ref = ref[:, :, b0 - lo // 4000: b0 - lo // 4000 + 10]
+            assert relerr(full[:, :, b0:b0 + 10].numpy(), ref.numpy()) <= TOL, (rc, b0)
