@@ -130,7 +130,7 @@ int orca_b200_module_kind(const orca_b200_module* m);
  * GPUs); pass 0, L/4000 for all.  `out` always addresses bin 0 of sample 0.
  * A shard may hold only a window of the sequence: x then addresses position `x_pos0` and
  * covers `x_len` positions (pass 0, L for the whole sequence); the window must contain
- * [bin_begin*4000 - 112004, bin_end*4000 + 112004) clipped to [0, L).
+ * [bin_begin*4000 - 112008, bin_end*4000 + 112012) clipped to [0, L).
  */
 size_t orca_b200_encoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L,
                                          int64_t chunk_bp);

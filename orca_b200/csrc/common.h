@@ -52,6 +52,8 @@ struct ConvLayer {
   size_t tc_w_bytes = 0;
   // odd extra input channel (129th / 65th channel of the Decoder combiners): w_extra[tap][c_out]
   float* w_extra = nullptr;
+  // bias that goes with tc_w when it differs from b (the composed lconv1 of the Encoder, conv_first_tc.cu)
+  float* tc_bias = nullptr;
 };
 
 // ---- generic conv (channel-last activations) -----------------------------------------

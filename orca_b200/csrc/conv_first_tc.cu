@@ -1,0 +1,250 @@
+// First encoder block on tensor cores: lconv1 = Conv1d(4,64,k9) BN Conv1d(64,64,k9) BN  (orca_modules.py:811-816)
+// has no nonlinearity, so away from the sequence ends it IS one Conv1d(4 -> 64, k = 17):
+//   y2[l] = bc + sum_{t<17} Wc[t] x[l + t - 8],  Wc[t] = sum_{t1+t2=t} W2f[t2] W1f[t1],  bc = b2f + sum_t2 W2f[t2] b1f
+// (W*f / b*f = BatchNorm-folded weights; composed in double precision on the host).  K = 17*4 = 68 -> 80, i.e.
+// 5 UMMA K-steps per 128-position tile instead of 36 for the 64->64 layer it replaces, and the 4->64
+// CUDA-core layer disappears.  The reference zero-pads the INTERMEDIATE activation, so the first/last 4
+// positions of the whole sequence differ from the composed conv; lconv1_edge_kernel recomputes those 8
+// positions exactly with the two separate layers (fp32).
+//
+// A operand: K index k = 4*tap + channel, so the 8 K-elements of chunk j for row l are the 8 consecutive
+// floats x[l + 2j - 8][0..3], x[l + 2j - 7][0..3] of the caller's channel-last input: the im2col tile
+// [10 chunks][128 rows][16 B] (bf16 hi and lo) is built by the CTA's 128 threads straight from global memory.
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "tc.h"
+#include "tc_device.cuh"
+
+namespace orca {
+namespace {
+using namespace tcdev;
+
+constexpr int kTaps = 17, kChunks = 10;  // 68 K-elements padded to 80
+
+__global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict__ x, long long sB, long long sC,
+                                                        long long sL, long long Ltot, long long l_begin, long long n,
+                                                        int npad, const uint8_t* __restrict__ wimg /*[10][128][16 B]*/,
+                                                        const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ out_hi,
+                                                        __nv_bfloat16* __restrict__ out_lo) {
+  extern __shared__ __align__(128) uint8_t dsm[];  // 3 x 20 KB operand images (dynamic: above the 48 KB static limit)
+  uint8_t* sAh = dsm;
+  uint8_t* sAl = dsm + kChunks * 128 * 16;
+  uint8_t* sBw = dsm + 2 * kChunks * 128 * 16;
+  __shared__ float sBias[64];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const long long t0 = (long long)blockIdx.x * 128;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < kChunks * 128; i += 128) reinterpret_cast<uint4*>(sBw)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+  if (tid < 64) sBias[tid] = bias[tid];
+
+  // im2col row of this thread: positions l-8 .. l+11 (20 positions x 4 channels), zero outside [0, Ltot)
+  {
+    const float* xb = x + (long long)b * sB;
+    const long long l = l_begin + t0 + tid;
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+      float v[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const long long p = l + 2 * j - 8 + h;
+        const bool ok = p >= 0 && p < Ltot;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[4 * h + c] = ok ? __ldg(xb + p * sL + c * sC) : 0.f;
+      }
+      split_store8(v, reinterpret_cast<__nv_bfloat16*>(sAh + (j * 128 + tid) * 16),
+                   reinterpret_cast<__nv_bfloat16*>(sAl + (j * 128 + tid) * 16));
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(64), idesc_cat = umma_idesc_bf16(128);
+      const uint32_t ah = umma_desc_lo(smem_u32(sAh), 2048), al = umma_desc_lo(smem_u32(sAl), 2048);
+      const uint32_t bw = umma_desc_lo(smem_u32(sBw), 2048);
+#pragma unroll
+      for (int ks = 0; ks < kChunks / 2; ++ks) {
+        const uint32_t o = ks * ((2 * 2048) >> 4);
+        umma_bf16(tmem, umma_desc64(ah + o), umma_desc64(bw + o), idesc_cat, ks > 0 ? 1u : 0u);  // [Ah*Bh | Ah*Bl]
+        umma_bf16(tmem, umma_desc64(al + o), umma_desc64(bw + o), idesc, 1u);                    // += Al*Bh
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const long long row = t0 + warp * 32 + lane;
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t r0[32], r1[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r0);
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, r1);
+    if (row < n) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) + sBias[c0 + j];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const size_t off = (((size_t)b * 8 + (c0 >> 3) + ch) * npad + row + 4) * 8;
+        split_store8(v + 8 * ch, out_hi + off, out_lo + off);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {  // pad rows of this sample's planes
+    const int tail0 = (int)n + 4, ntail = npad - tail0, per_plane = 4 + ntail;
+    for (int i = tid; i < 8 * per_plane; i += 128) {
+      const int p = i / per_plane, j = i - p * per_plane;
+      const size_t r = ((size_t)b * 8 + p) * npad + (j < 4 ? j : tail0 + (j - 4));
+      reinterpret_cast<uint4*>(out_hi)[r] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(out_lo)[r] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// Exact two-layer evaluation of the 4 positions next to one end of the sequence (see file header).
+// grid (2 ends, nb), 64 threads = output channels.  w1 [9][4][64], w2 [9][64][64] (folded, fp32).
+__global__ void __launch_bounds__(64) lconv1_edge_kernel(const float* __restrict__ x, long long sB, long long sC,
+                                                         long long sL, long long Ltot, long long l_begin, long long n,
+                                                         int npad, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  __shared__ float y1[8][64];
+  const int co = threadIdx.x, end = blockIdx.x, b = blockIdx.y;
+  const long long p0 = end == 0 ? 0 : Ltot - 8;  // first of the 8 intermediate positions needed
+  const long long l0 = end == 0 ? 0 : Ltot - 4;  // first of the 4 output positions
+  if (l0 < l_begin || l0 + 4 > l_begin + n) return;  // this window does not own that end
+  const float* xb = x + (long long)b * sB;
+  for (int i = 0; i < 8; ++i) {
+    float acc = b1[co];
+    for (int t = 0; t < 9; ++t) {
+      const long long p = p0 + i + t - 4;
+      if (p < 0 || p >= Ltot) continue;
+      for (int c = 0; c < 4; ++c) acc = fmaf(__ldg(xb + p * sL + c * sC), w1[(t * 4 + c) * 64 + co], acc);
+    }
+    y1[i][co] = acc;
+  }
+  __syncthreads();
+  for (int i = 0; i < 4; ++i) {
+    const long long l = l0 + i;
+    float acc = b2[co];
+    for (int t = 0; t < 9; ++t) {
+      const long long p = l + t - 4;
+      if (p < 0 || p >= Ltot) continue;  // zero padding of the INTERMEDIATE activation
+      const int pi = (int)(p - p0);
+      for (int m = 0; m < 64; ++m) acc = fmaf(y1[pi][m], w2[(t * 64 + m) * 64 + co], acc);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+    const size_t off = (((size_t)b * 8 + (co >> 3)) * npad + (size_t)(l - l_begin) + 4) * 8 + (co & 7);
+    out_hi[off] = h;
+    out_lo[off] = __float2bfloat16_rn(acc - __bfloat162float(h));
+  }
+}
+
+uint16_t bits_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bits_f32(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+}  // namespace
+
+// w1 [9][4][64], b1 [64], w2 [9][64][64], b2 [64]: BatchNorm-folded fp32 weights of lconv1[0], lconv1[1]
+int tc_pack_lconv1(ConvLayer& L0, const float* w1, const float* b1, const float* w2, const float* b2,
+                   std::vector<void*>& allocs) {
+  std::vector<double> wc((size_t)kTaps * 4 * 64, 0.0), bc(64);
+  for (int co = 0; co < 64; ++co) {
+    double acc = b2[co];
+    for (int t2 = 0; t2 < 9; ++t2)
+      for (int m = 0; m < 64; ++m) acc += (double)w2[((size_t)t2 * 64 + m) * 64 + co] * (double)b1[m];
+    bc[co] = acc;
+  }
+  for (int t2 = 0; t2 < 9; ++t2)
+    for (int t1 = 0; t1 < 9; ++t1)
+      for (int c = 0; c < 4; ++c)
+        for (int m = 0; m < 64; ++m) {
+          const double a = w1[((size_t)t1 * 4 + c) * 64 + m];
+          const float* w2r = w2 + ((size_t)t2 * 64 + m) * 64;
+          double* dst = &wc[((size_t)(t1 + t2) * 4 + c) * 64];
+          for (int co = 0; co < 64; ++co) dst[co] += a * (double)w2r[co];
+        }
+  std::vector<uint16_t> img((size_t)kChunks * 128 * 8, 0);  // [chunk][Bh rows 0..63 | Bl rows 64..127][8]
+  for (int j = 0; j < kChunks; ++j)
+    for (int co = 0; co < 64; ++co)
+      for (int e = 0; e < 8; ++e) {
+        const int k = j * 8 + e, t = k / 4, c = k % 4;
+        const float v = t < kTaps ? (float)wc[((size_t)t * 4 + c) * 64 + co] : 0.f;
+        const uint16_t h = bits_rn(v);
+        img[((size_t)j * 128 + co) * 8 + e] = h;
+        img[((size_t)j * 128 + 64 + co) * 8 + e] = bits_rn(v - bits_f32(h));
+      }
+  std::vector<float> bf(64);
+  for (int i = 0; i < 64; ++i) bf[i] = (float)bc[i];
+  void* d = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&d, img.size() * 2));
+  allocs.push_back(d);
+  ORCA_CUDA_OK(cudaMemcpy(d, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  void* db = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&db, 64 * sizeof(float)));
+  allocs.push_back(db);
+  ORCA_CUDA_OK(cudaMemcpy(db, bf.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+  L0.tc_w = d;
+  L0.tc_w_bytes = img.size() * 2;
+  L0.tc_bias = static_cast<float*>(db);
+  return ORCA_B200_OK;
+}
+
+int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
+              int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s) {
+  if (!L0.tc_w || !L0.tc_bias || L0.c_in != 4 || L0.c_out != 64 || L1.c_in != 64 || L1.c_out != 64 || out->C != 64 ||
+      out->n != n || out->nb != nb) {
+    set_error("tc_lconv1: bad layers / geometry");
+    return ORCA_B200_EINVAL;
+  }
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb);
+  constexpr int kSmem = 3 * kChunks * 128 * 16;
+  static bool configured = false;
+  if (!configured) {
+    ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  lconv1_tc_kernel<<<grid, 128, kSmem, s>>>(x, sB, sC, sL, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
+                                        L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
+  ORCA_LAUNCH_OK();
+  if (l_begin == 0 || l_begin + n == Ltot) {
+    lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(x, sB, sC, sL, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,
+                                                            static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
+    ORCA_LAUNCH_OK();
+  }
+  return ORCA_B200_OK;
+}
+
+}  // namespace orca

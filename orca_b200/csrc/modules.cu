@@ -251,12 +251,17 @@ static int encoder_window_tc(const ConvLayer* L, const float* x, int64_t sB, int
       const ConvLayer* Lk = L + 4 * k;
       const int C = Lk[0].c_out;
       TcAct t0 = tc_make(X[0], nb, C, len), t1 = tc_make(X[1], nb, C, len), t2 = tc_make(X[2], nb, C, len);
-      if (k == 0) {
-        ORCA_TRY(tc_conv_first(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, &t0, s));
+      if (k == 0 && Lk[0].tc_w) {
+        // lconv1 (two linear convs) as ONE composed k=17 tensor-core conv straight from the input (conv_first_tc.cu)
+        ORCA_TRY(tc_lconv1(Lk[0], Lk[1], x, sB, sC, sL, nb, Ltot, l_begin, n, &t1, s));
       } else {
-        ORCA_TRY(tc_conv1d(Lk[0], in, nullptr, &t0, nullptr, 1, 0, s));
+        if (k == 0) {
+          ORCA_TRY(tc_conv_first(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, &t0, s));
+        } else {
+          ORCA_TRY(tc_conv1d(Lk[0], in, nullptr, &t0, nullptr, 1, 0, s));
+        }
+        ORCA_TRY(tc_conv1d(Lk[1], t0, nullptr, &t1, nullptr, 1, 0, s));  // lout_k
       }
-      ORCA_TRY(tc_conv1d(Lk[1], t0, nullptr, &t1, nullptr, 1, 0, s));  // lout_k
       ORCA_TRY(tc_conv1d(Lk[2], t1, nullptr, &t0, nullptr, 1, 1, s));
       if (k == 6) {  // out7 only, fp32 channel-last (orca_modules.py:949-950)
         ORCA_TRY(tc_conv1d(Lk[3], t0, nullptr, nullptr, out7, 1, 1, s));
@@ -739,7 +744,8 @@ static int upload(const std::vector<float>& h, float** d, std::vector<void*>& al
   return ORCA_B200_OK;
 }
 
-static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<void*>& allocs) {
+static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<void*>& allocs,
+                      std::vector<float>* keep_w = nullptr, std::vector<float>* keep_b = nullptr) {
   const int taps = p.kh * p.kw;
   const bool odd = (p.c_in == 129 || p.c_in == 65);
   const int cin_main = odd ? p.c_in - 1 : p.c_in;
@@ -772,6 +778,8 @@ static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<
   if (odd) ORCA_TRY(upload(wx, &L.w_extra, allocs));
   ORCA_TRY(tc_pack_layer(L, w.data(), allocs));
   ORCA_TRY(tc_pack_layer2d(L, w.data(), allocs));
+  if (keep_w) *keep_w = w;
+  if (keep_b) *keep_b = bias;
   return ORCA_B200_OK;
 }
 
@@ -845,8 +853,12 @@ int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_
   m->kind = kind; m->flags = flags; m->num_1d = num_1d;
   if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); delete m; set_error("module_create: no CUDA device"); return ORCA_B200_ECUDA; }
   m->L.resize(n_convs);
+  std::vector<float> head_w[2], head_b[2];
   for (int i = 0; i < n_convs; ++i) {
-    int st = pack_layer(convs[i], m->L[i], m->allocs);
+    const bool enc_head = (kind == ORCA_B200_ENCODER || kind == ORCA_B200_NET) && i < 2;  // lconv1[0], lconv1[1]
+    int st = pack_layer(convs[i], m->L[i], m->allocs, enc_head ? &head_w[i] : nullptr, enc_head ? &head_b[i] : nullptr);
+    if (st == ORCA_B200_OK && enc_head && i == 1)
+      st = tc_pack_lconv1(m->L[0], head_w[0].data(), head_b[0].data(), head_w[1].data(), head_b[1].data(), m->allocs);
     if (st != ORCA_B200_OK) { orca_b200_module_destroy(m); return st; }
   }
   *out = m;
@@ -885,7 +897,7 @@ int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t
   ORCA_TRY(check_ptr_device(out, "encoder: out"));
   ORCA_TRY(check_ptr_device(workspace, "encoder: workspace"));
   {  // the window x covers must contain everything the requested bins read
-    int64_t need0 = bin_begin * kBin - kHaloBins * kBin - 4, need1 = bin_end * kBin + kHaloBins * kBin + 4;
+    int64_t need0 = bin_begin * kBin - kHaloBins * kBin - 8, need1 = bin_end * kBin + kHaloBins * kBin + 12;
     if (need0 < 0) need0 = 0;
     if (need1 > L) need1 = L;
     if (x_pos0 < 0 || x_len <= 0 || (bin_begin < bin_end && (x_pos0 > need0 || x_pos0 + x_len < need1))) {
