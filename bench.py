@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--seq-len", type=int, default=SEQ_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-bp", type=int, default=0, help="encoder chunk length in bp (0 = library default)")
+    ap.add_argument("--concurrent-strands", action="store_true", help="encode the two strands on two CUDA streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,8 +189,10 @@ def main():
     L = args.seq_len
 
     shell = models.H1esc(seed=0, device=dev)
+    shell.net0.chunk_bp = args.chunk_bp
     seq_host = torch.from_numpy(synthetic.random_sequence(1, L, 0)).pin_memory()
     runner = parallel.ShardedForward(shell, L, rank, world, dev)
+    runner.concurrent_strands = args.concurrent_strands
     runner.upload(seq_host)  # device-resident input for the `value` leg
     mpos = wpos = L // 2
 

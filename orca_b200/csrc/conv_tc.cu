@@ -221,15 +221,32 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_sample, t = tile - b * a.tiles_per_sample;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      mbar_wait(bAcc_full + 8 * as, aph);
-      tc_fence_after();
       const int l = t * 128 + q * 32 + lane;  // position within the sample
       const bool valid = l < a.n;
       const size_t r_in = (size_t)l + 4;
-#pragma unroll 1
+      // residual(s) of a 32-channel group, fetched one group ahead (the first one before the accumulator
+      // wait) so that their HBM/L2 latency overlaps the tile's MMAs instead of serialising the epilogue
+      auto load_res = [&](int c0, float* dst) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = 0.f;
+        if (a.res_hi && valid) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_in + r_in) * 8;
+            add_hilo8(dst + 8 * ch, a.res_hi + off, a.res_lo + off);
+            if (a.res2_hi) add_hilo8(dst + 8 * ch, a.res2_hi + off, a.res2_lo + off);
+          }
+        }
+      };
+      float rcur[32];
+      load_res(0, rcur);
+      mbar_wait(bAcc_full + 8 * as, aph);
+      tc_fence_after();
+#pragma unroll
       for (int c0 = 0; c0 < C_OUT; c0 += 32) {
         uint32_t raw[32];
-        float v[32];
+        float v[32], rnext[32];
+        if (c0 + 32 < C_OUT) load_res(c0 + 32, rnext);
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + c0, raw);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -243,13 +260,11 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
           const float x = v[j] + sBias[c0 + j];
           v[j] = a.relu ? fmaxf(x, 0.f) : x;
         }
-        if (a.res_hi && valid) {
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_in + r_in) * 8;
-            add_hilo8(v + 8 * ch, a.res_hi + off, a.res_lo + off);
-            if (a.res2_hi) add_hilo8(v + 8 * ch, a.res2_hi + off, a.res2_lo + off);
-          }
+        for (int j = 0; j < 32; ++j) v[j] += rcur[j];
+        if (c0 + 32 < C_OUT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
         }
         if (a.pool > 1) {
 #pragma unroll

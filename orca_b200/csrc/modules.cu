@@ -297,7 +297,7 @@ static int encoder_window_any(const ConvLayer* L, const float* x, int64_t sB, in
 }
 
 static const int64_t kBin = 4000, kHaloBins = 28;  // x_padding = 112000, orca_modules.py:931-932
-static const int64_t kDefaultChunkBp = 4000000;
+static const int64_t kDefaultChunkBp = 16000000;  // ~13.5 GB of workspace; 2 chunks per 32 Mb strand
 
 static int encoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
                        int64_t sL, float* out, int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, Arena& ar,

@@ -45,6 +45,7 @@ class ShardedForward:
         self.b0, self.b1 = shard_bins(self.P, rank, world)
         self.s0, self.s1 = shard_window(L, self.b0, self.b1)
         self.window = None
+        self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         self.h2d_bytes = 0
         self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
 
@@ -55,13 +56,18 @@ class ShardedForward:
         self.h2d_bytes = sl.numel() * 4
         return self.window
 
-    def _encode(self, reverse):
-        P, n = self.P, self.b1 - self.b0
-        enc = torch.empty((1, P, 128), dtype=torch.float32, device=self.device)
-        bins = (P - self.b1, P - self.b0) if reverse else (self.b0, self.b1)
+    def _encode_local(self, reverse):
+        """This rank's bins of one strand -> (1, P, 128) buffer (other bins undefined)."""
+        enc = torch.empty((1, self.P, 128), dtype=torch.float32, device=self.device)
+        bins = (self.P - self.b1, self.P - self.b0) if reverse else (self.b0, self.b1)
         self.shell.net0(self.window.transpose(1, 2), bin_range=bins, out=enc, reverse_complement=reverse,
                         window=(self.s0, self.L))
+        return enc
+
+    def _gather(self, enc, reverse):
+        P, n = self.P, self.b1 - self.b0
         if self.world > 1:
+            bins = (P - self.b1, P - self.b0) if reverse else (self.b0, self.b1)
             mine = enc[0, bins[0]:bins[1]].contiguous()
             gathered = torch.empty((self.world * n, 128), dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(gathered, mine)  # concatenation along dim 0 (NCCL and gloo agree)
@@ -71,19 +77,35 @@ class ShardedForward:
             enc = gathered.reshape(1, P, 128)
         return enc.transpose(1, 2)
 
+    def _encode(self, reverse):
+        return self._gather(self._encode_local(reverse), reverse)
+
     def forward(self, mpos, wpos):
         """Returns the 6 strand-averaged maps (6, 250, 250) on rank 0 (None elsewhere)."""
         shell, world, rank = self.shell, self.world, self.rank
         with torch.no_grad():
-            enc_f = self._encode(False)
-            enc_r = self._encode(True)
+            if self.concurrent_strands and self.device.type == "cuda":
+                # the two strands' encoders are independent: two streams let one strand's small late-stage
+                # kernels and launch gaps hide behind the other's big ones; the collectives stay on one stream
+                loc_f, loc_r = predict.run_concurrent([lambda: self._encode_local(False), lambda: self._encode_local(True)],
+                                                      self.device)
+            else:
+                loc_f, loc_r = self._encode_local(False), self._encode_local(True)
+            enc_f, enc_r = self._gather(loc_f, False), self._gather(loc_r, True)
             rev_rank = 1 if world > 1 else 0
             preds = {}
-            for reverse, owner, enc in ((False, 0, enc_f), (True, rev_rank, enc_r)):
-                if rank == owner:
-                    encs = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc)))
-                    p, _ = predict.cascade_32mb(shell, encs, 1, mpos, wpos, reverse)
-                    preds[reverse] = torch.cat([t[0] for t in p], 0)  # (6, 250, 250)
+
+            def cascade(reverse, enc):
+                encs = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc)))
+                p, _ = predict.cascade_32mb(shell, encs, 1, mpos, wpos, reverse)
+                return torch.cat([t[0] for t in p], 0)  # (6, 250, 250)
+
+            mine = [(rev, enc) for rev, owner, enc in ((False, 0, enc_f), (True, rev_rank, enc_r)) if rank == owner]
+            # independent strand cascades on separate CUDA streams: each decoder conv is a ~20 us launch whose
+            # prologue/tail latency the other stream's kernels fill
+            outs = predict.run_concurrent([lambda r=r, e=e: cascade(r, e) for r, e in mine], self.device)
+            for (rev, _), o in zip(mine, outs):
+                preds[rev] = o
             if world > 1:
                 if rank == rev_rank:
                     dist.send(preds[True], dst=0)

@@ -49,6 +49,40 @@ def _log_normmat(model, level, device):
     return cache[key]
 
 
+_SIDE_STREAMS = {}
+
+
+def run_concurrent(jobs, device):
+    """Run independent GPU jobs (callables returning tensors) on separate CUDA streams and join them on the
+    current stream.  The decoder cascades of different (model, strand) pairs are independent chains of ~20 us
+    kernels; interleaving two chains hides each launch's prologue/tail latency behind the other's work."""
+    if len(jobs) <= 1:
+        return [job() for job in jobs]
+    main = torch.cuda.current_stream(device)
+    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    while len(pool) < len(jobs):
+        pool.append(torch.cuda.Stream(device=device))
+    results = []
+    for job, st in zip(jobs, pool):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            results.append(job())
+    for st in pool[:len(jobs)]:
+        main.wait_stream(st)
+
+    def mark(obj):  # outputs were allocated on a side stream but live on with the main stream
+        if isinstance(obj, torch.Tensor):
+            obj.record_stream(main)
+        elif isinstance(obj, (list, tuple)):
+            for o in obj:
+                mark(o)
+        elif isinstance(obj, dict):
+            for o in obj.values():
+                mark(o)
+    mark(results)
+    return results
+
+
 def encode_strand(model, seq_dev, reverse):
     """net0 on one strand of the uploaded (B, L, 4) tensor."""
     return model.net0(seq_dev.transpose(1, 2), reverse_complement=reverse)
@@ -101,14 +135,18 @@ def genomepredict(sequence, mchr, mpos=-1, wpos=-1, models=(), targets=None, ann
     with torch.no_grad(), torch.cuda.device(device):
         seq_dev = _to_device_sequence(sequence, device)
         B = seq_dev.shape[0]
-        per_strand, starts0 = [], None
-        for reverse in (False, True):
-            for model in models:
-                encs = dict(zip([1, 2, 4, 8, 16, 32], model.net(encode_strand(model, seq_dev, reverse))))
-                preds, starts = cascade_32mb(model, encs, B, mpos, wpos, reverse)
-                per_strand.append(preds)
-                if not reverse and starts0 is None:
-                    starts0 = starts
+        # encoders saturate the GPU on their own: run them back to back; the (model, strand) cascades are
+        # independent latency-bound chains: run them concurrently
+        passes = [(reverse, model) for reverse in (False, True) for model in models]
+        enc4k = [encode_strand(model, seq_dev, reverse) for reverse, model in passes]
+
+        def cascade(reverse, model, e):
+            encs = dict(zip([1, 2, 4, 8, 16, 32], model.net(e)))
+            return cascade_32mb(model, encs, B, mpos, wpos, reverse)
+
+        results = run_concurrent([lambda r=r, m=m, e=e: cascade(r, m, e) for (r, m), e in zip(passes, enc4k)], device)
+        per_strand = [preds for preds, _ in results]
+        starts0 = results[0][1]
         n = len(models)
         stacked = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])) for i in range(n)]
         host = [s.cpu().numpy() for s in stacked]
