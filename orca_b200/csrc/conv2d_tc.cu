@@ -23,6 +23,8 @@ namespace {
 using namespace tcdev;
 
 constexpr int kPX = 64;  // zero pixels on each side of an image row
+constexpr int kEpiWarps = 8;                   // two per TMEM lane quarter (the epilogue is latency bound per warp)
+constexpr int kThreads2d = 64 + 32 * kEpiWarps;
 
 struct Tc2dKArgs {
   const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t aLo, uint3
 }
 
 template <int C_OUT, int KSTEPS>
-__global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
+__global__ void __launch_bounds__(kThreads2d, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int NA = a.NA, NW = a.NW;
   uint8_t* sA = smem;
@@ -80,14 +82,14 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(bA_full + 8 * i, 1); mbar_init(bA_empty + 8 * i, 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(bW_full + 8 * i, 1); mbar_init(bW_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < C_OUT; i += 192) sBias[i] = a.bias[i];
+  for (int i = tid; i < C_OUT; i += kThreads2d) sBias[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,7 +189,9 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
     }
   } else {
     // ================= epilogue =================
-    const int q = warp & 3;
+    // warp (q, h): TMEM lane quarter q, 16-column units h, h+2, ... of the C_OUT output channels
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    constexpr int UNITS = C_OUT / 16, MYU = UNITS / 2;  // units per warp (1 or 2)
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
@@ -199,32 +203,37 @@ __global__ void __launch_bounds__(192, 1) conv2d_tc_kernel(const Tc2dKArgs a) {
       const bool valid = x < a.S;
       const long long r = (long long)y * a.Wp + kPX + x;
       // residual fetched BEFORE waiting for the accumulator: its L2 latency overlaps the tile's MMAs
-      float res[C_OUT];
+      float res[MYU][16];
 #pragma unroll
-      for (int j = 0; j < C_OUT; ++j) res[j] = 0.f;
-      if (a.res_hi && valid) {
+      for (int u = 0; u < MYU; ++u) {
 #pragma unroll
-        for (int ch = 0; ch < C_OUT / 8; ++ch) {
-          const long long off = (((long long)b * (C_OUT / 8) + ch) * a.plane_rows + r) * 8;
-          add_hilo8(res + 8 * ch, a.res_hi + off, a.res_lo + off);
+        for (int j = 0; j < 16; ++j) res[u][j] = 0.f;
+        if (a.res_hi && valid) {
+          const int c0 = 16 * (h + 2 * u);
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const long long off = (((long long)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.plane_rows + r) * 8;
+            add_hilo8(res[u] + 8 * ch, a.res_hi + off, a.res_lo + off);
+          }
         }
       }
       mbar_wait(bAcc_full + 8 * as, aph);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < C_OUT; c0 += 32) {
-        uint32_t raw[32], raw2[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + C_OUT + c0, raw2);
+      for (int u = 0; u < MYU; ++u) {
+        const int c0 = 16 * (h + 2 * u);
+        uint32_t raw[16], raw2[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + C_OUT + c0, raw2);
         if (valid) {
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const float t = __uint_as_float(raw[j]) + __uint_as_float(raw2[j]) + sBias[c0 + j];
-            v[j] = (a.relu ? fmaxf(t, 0.f) : t) + res[c0 + j];
+            v[j] = (a.relu ? fmaxf(t, 0.f) : t) + res[u][j];
           }
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < 2; ++ch) {
             const long long off = (((long long)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.plane_rows + r) * 8;
             split_store8(v + 8 * ch, a.out_hi + off, a.out_lo + off);
           }
@@ -435,9 +444,9 @@ int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out,
     ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  if (L.c_out == 32 && kc == 8) conv2d_tc_kernel<32, 4><<<grid, 192, smem, s>>>(a);
-  else if (L.c_out == 64 && kc == 8) conv2d_tc_kernel<64, 4><<<grid, 192, smem, s>>>(a);
-  else if (L.c_out == 64 && kc == 4) conv2d_tc_kernel<64, 2><<<grid, 192, smem, s>>>(a);
+  if (L.c_out == 32 && kc == 8) conv2d_tc_kernel<32, 4><<<grid, kThreads2d, smem, s>>>(a);
+  else if (L.c_out == 64 && kc == 8) conv2d_tc_kernel<64, 4><<<grid, kThreads2d, smem, s>>>(a);
+  else if (L.c_out == 64 && kc == 4) conv2d_tc_kernel<64, 2><<<grid, kThreads2d, smem, s>>>(a);
   else { set_error("tc_conv2d: no kernel for %d->%d", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;

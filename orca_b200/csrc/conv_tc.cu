@@ -39,6 +39,8 @@ using namespace tcdev;
 constexpr int kRows = 136;                       // 128 output rows + 8 halo rows per A slot
 constexpr int kASlotBytes = 2 * 8 * kRows * 16;  // hi + lo images of a 64-channel K-block
 constexpr int kALoOff = 8 * kRows * 16;
+constexpr int kEpiWarps = 8;                    // two per TMEM lane quarter, each takes every other 32-column group
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 producer, warp 1 MMA issuer, then the epilogue warps
 
 struct TcKArgs {
   const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;
@@ -73,7 +75,7 @@ struct TcCfg {
 // CONCAT: the two products that share A = Ah run as ONE MMA against B = [Bh;Bl] (N = 2*C_OUT, two
 // accumulator column blocks summed in the epilogue) -- 2 MMAs and 2 A-operand reads per K step instead of 3.
 template <int C_IN, int C_OUT, bool CONCAT>
-__global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a) {
   using Cfg = TcCfg<C_IN, C_OUT>;
   constexpr int NKB = Cfg::NKB, NW = Cfg::NW, NA = Cfg::NA;
   constexpr bool RESIDENT = Cfg::RESIDENT;
@@ -94,14 +96,14 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(bA_full + 8 * i, 1); mbar_init(bA_empty + 8 * i, 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(bW_full + 8 * i, 1); mbar_init(bW_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < C_OUT; i += 192) sBias[i] = a.bias[i];
+  for (int i = tid; i < C_OUT; i += kThreads) sBias[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -204,13 +206,15 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
     }
   } else {
     // ================= epilogue warps (TMEM lane quarter = warp % 4) =================
-    const int q = warp & 3;
+    // The epilogue is instruction-latency bound per warp (one warp per scheduler, long dependent chains), so
+    // two warps share each lane quarter: warp (q, h) handles the 32-column groups h, h+2, ...
+    const int q = warp & 3, h = (warp - 2) >> 2;
     if (blockIdx.x == 0 && a.out_hi) {  // zero the pad rows of the output planes (they are the next layer's padding)
       const int et = (warp - 2) * 32 + lane;
       const int planes = a.nb * (C_OUT / 8);
       const int tail0 = a.n_out + 4, ntail = a.npad_out - tail0;
       const int per_plane = 4 + ntail;
-      for (int i = et; i < planes * per_plane; i += 128) {
+      for (int i = et; i < planes * per_plane; i += 32 * kEpiWarps) {
         const int p = i / per_plane, j = i - p * per_plane;
         const size_t r = (size_t)p * a.npad_out + (j < 4 ? j : tail0 + (j - 4));
         reinterpret_cast<uint4*>(a.out_hi)[r] = make_uint4(0, 0, 0, 0);
@@ -239,14 +243,16 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
         }
       };
       float rcur[32];
-      load_res(0, rcur);
+      if (32 * h < C_OUT) load_res(32 * h, rcur);
       mbar_wait(bAcc_full + 8 * as, aph);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+      for (int g = 0; g < (C_OUT + 63) / 64; ++g) {
+        const int c0 = 32 * h + 64 * g;
+        if (c0 >= C_OUT) break;
         uint32_t raw[32];
         float v[32], rnext[32];
-        if (c0 + 32 < C_OUT) load_res(c0 + 32, rnext);
+        if (c0 + 64 < C_OUT) load_res(c0 + 64, rnext);
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + c0, raw);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const TcKArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += rcur[j];
-        if (c0 + 32 < C_OUT) {
+        if (c0 + 64 < C_OUT) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
         }
@@ -308,7 +314,7 @@ int launch_tc_impl(const TcKArgs& a, int sms, cudaStream_t s) {
     configured = true;
   }
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv1d_tc_kernel<C_IN, C_OUT, CONCAT><<<grid, 192, Cfg::SMEM, s>>>(a);
+  conv1d_tc_kernel<C_IN, C_OUT, CONCAT><<<grid, kThreads, Cfg::SMEM, s>>>(a);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }

@@ -9,6 +9,6 @@ ncu --set full --clock-control none --import-source on -k regex:conv1d_tc_kernel
     python tools/ncu_target.py > gpurun_out/ncu_conv1d.log 2>&1
 NCU_REPS=0 ncu --set full --clock-control none --import-source on -k regex:conv2d_tc_kernel -s 30 -c 6 -f \
     -o gpurun_out/prof_conv2d python tools/ncu_target.py > gpurun_out/ncu_conv2d.log 2>&1
-ncu --set full --clock-control none -k regex:conv_first -c 1 -f -o gpurun_out/prof_first \
+ncu --set full --clock-control none -k regex:lconv1_tc -c 1 -f -o gpurun_out/prof_first \
     python tools/ncu_target.py > gpurun_out/ncu_first.log 2>&1
-tail -1 gpurun_out/ncu_*.log
+for f in gpurun_out/ncu_*.log; do tail -n 1 $f; done
