@@ -51,23 +51,36 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
   for (int i = tid; i < kChunks * 128; i += 128) reinterpret_cast<uint4*>(sBw)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
   if (tid < 64) sBias[tid] = bias[tid];
 
-  // im2col row of this thread: positions l-8 .. l+11 (20 positions x 4 channels), zero outside [0, Ltot)
+  // stage the 148 input positions of the tile (l0-8 .. l0+139; zero outside [0, Ltot)) once, coalesced ...
+  __shared__ __align__(16) float sX[148][4];
   {
     const float* xb = x + (long long)b * sB;
-    const long long l = l_begin + t0 + tid;
-#pragma unroll
-    for (int j = 0; j < kChunks; ++j) {
-      float v[8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const long long p = l + 2 * j - 8 + h;
-        const bool ok = p >= 0 && p < Ltot;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[4 * h + c] = ok ? __ldg(xb + p * sL + c * sC) : 0.f;
+    for (int i = tid; i < 148; i += 128) {
+      const long long p = l_begin + t0 - 8 + i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p >= 0 && p < Ltot) {
+        const bool vec_ok = ((sL & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb + (sC == -1 ? -3 : 0)) & 15) == 0);
+        if (sC == 1 && vec_ok) {  // channel-last memory: one 16-byte load per position
+          v = __ldg(reinterpret_cast<const float4*>(xb + p * sL));
+        } else if (sC == -1 && vec_ok) {  // reverse-complement walk of channel-last memory: channels stored descending
+          const float4 r = __ldg(reinterpret_cast<const float4*>(xb + p * sL - 3));
+          v = make_float4(r.w, r.z, r.y, r.x);
+        } else {
+          v = make_float4(__ldg(xb + p * sL), __ldg(xb + p * sL + sC), __ldg(xb + p * sL + 2 * sC), __ldg(xb + p * sL + 3 * sC));
+        }
       }
-      split_store8(v, reinterpret_cast<__nv_bfloat16*>(sAh + (j * 128 + tid) * 16),
-                   reinterpret_cast<__nv_bfloat16*>(sAl + (j * 128 + tid) * 16));
+      *reinterpret_cast<float4*>(&sX[i][0]) = v;
     }
+  }
+  __syncthreads();
+  // ... then the im2col row of this thread: chunk j = positions (tid + 2j, tid + 2j + 1) of the staged tile
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const float4 p0 = *reinterpret_cast<const float4*>(&sX[tid + 2 * j][0]);
+    const float4 p1 = *reinterpret_cast<const float4*>(&sX[tid + 2 * j + 1][0]);
+    const float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    split_store8(v, reinterpret_cast<__nv_bfloat16*>(sAh + (j * 128 + tid) * 16),
+                 reinterpret_cast<__nv_bfloat16*>(sAl + (j * 128 + tid) * 16));
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
