@@ -92,6 +92,13 @@ const char* orca_b200_version(void);
 const char* orca_b200_last_error(void);
 int orca_b200_set_impl(int impl);
 int orca_b200_get_impl(void);
+/*
+ * Decoder scheduling.  1 (default): all 3x3 convs of a decoder call run as ONE persistent cooperative kernel
+ * with grid barriers between layers (lowest latency for a single cascade).  0: one launch per conv, which lets
+ * independent cascades on different CUDA streams interleave (cooperative kernels would serialise).
+ * -1 restores the default.  Returns the previous setting.
+ */
+int orca_b200_set_decoder_program(int on);
 /* number of kernel launches issued by this library since load (all threads) */
 uint64_t orca_b200_launch_count(void);
 

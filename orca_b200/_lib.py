@@ -34,6 +34,7 @@ SIGNATURES = {
     "orca_b200_set_impl": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_get_impl": (ctypes.c_int, []),
     "orca_b200_launch_count": (ctypes.c_uint64, []),
+    "orca_b200_set_decoder_program": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_profile_summary": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64]),
     "orca_b200_module_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ConvParams), ctypes.c_int32,

@@ -570,7 +570,23 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
 }
 
 // ---- the same decoder programs on the tcgen05 path (activations as bf16 hi/lo map planes, tc.h) ----
+// When a decoder program is being recorded (conv2d_prog.cu) the conv is appended to it instead of launched.
+static thread_local Tc2dProgram* t_prog = nullptr;
+
+// -1 = take the default (env ORCA_B200_DEC_PROGRAM, else on); set by orca_b200_set_decoder_program
+static std::atomic<int> g_dec_program{-1};
+
+static bool use_decoder_program() {
+  int v = g_dec_program.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("ORCA_B200_DEC_PROGRAM");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static int tc_conv2d_prof(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s) {
+  if (t_prog) return t_prog->add(L, in, res, out, relu);
   if (!g_profile.load(std::memory_order_relaxed)) return tc_conv2d(L, in, res, out, relu, s);
   ProfRec r;
   ORCA_CUDA_OK(cudaEventCreate(&r.e0));
@@ -624,14 +640,36 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
   rot.buf[0] = ar.raw(b64); rot.buf[1] = ar.raw(b64); rot.buf[2] = ar.raw(b64);
   void* hbuf = ar.raw(b64);
   void* ebuf = is_1m ? nullptr : ar.raw(b64);
+  void* ebuf2 = is_1m ? nullptr : ar.raw(b64);  // coarse-map term (kept apart from the distance term: both are
+                                                // computed before the conv program runs)
   float* tmp = ar.f32((size_t)B * S * S);
+  const size_t prog_bytes = Tc2dProgram::scratch_bytes(128);
+  void* prog_scratch = ar.raw(prog_bytes);
   ARENA_OK(ar);
   if (!ar.dry) {
+    Tc2dProgram prog;
+    struct ProgGuard { ~ProgGuard() { t_prog = nullptr; } } guard;  // never leave a dangling recorder on error paths
+    t_prog = use_decoder_program() ? &prog : nullptr;
+    auto flush = [&]() -> int {  // run the recorded convs (program mode) before anything reads their output
+      if (!t_prog) return ORCA_B200_OK;
+      t_prog = nullptr;
+      if (!g_profile.load(std::memory_order_relaxed)) return prog.run(prog_scratch, prog_bytes, s);
+      ProfRec r;
+      ORCA_CUDA_OK(cudaEventCreate(&r.e0));
+      ORCA_CUDA_OK(cudaEventCreate(&r.e1));
+      ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
+      const int st = prog.run(prog_scratch, prog_bytes, s);
+      ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
+      r.c_in = -1; r.c_out = prog.size(); r.taps = 9; r.dil = 1; r.tc = 1; r.flop = prog.flop();
+      g_prof.push_back(r);
+      return st;
+    };
     // pad pixels of every map must be zero; the layers only ever write valid pixels
     ORCA_CUDA_OK(cudaMemsetAsync(matb, 0, 2 * b64, s));
     for (int i = 0; i < 3; ++i) ORCA_CUDA_OK(cudaMemsetAsync(rot.buf[i], 0, b64, s));
     ORCA_CUDA_OK(cudaMemsetAsync(hbuf, 0, b64, s));
     if (ebuf) ORCA_CUDA_OK(cudaMemsetAsync(ebuf, 0, b64, s));
+    if (ebuf2) ORCA_CUDA_OK(cudaMemsetAsync(ebuf2, 0, b64, s));
     TcMap mat = map_make(matb, B, 128, S);
     ORCA_TRY(tc_outer_sum(xcl, &mat, s));
     TcMap cur;
@@ -640,6 +678,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       ORCA_TRY(bottleneck_tc(L + D1M_LCONV, L + D1M_CONV, cur, false, rot, hbuf, s));
       for (int i = 1; i < 19; ++i)
         ORCA_TRY(bottleneck_tc(L + D1M_LCONV + 2 * i, L + D1M_CONV + 2 * i, cur, true, rot, hbuf, s));
+      ORCA_TRY(flush());
       ORCA_TRY(tc_final_head_tmp(cur, L[D1M_FINAL], L[D1M_FINAL + 1], tmp, s));
     } else {
       TcMap E = map_make(ebuf, B, 64, S);
@@ -655,9 +694,10 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       cur = a3;
       if (y) {
         const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
-        ORCA_TRY(tc_extra_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, &E, mode, s));
+        TcMap E2 = map_make(ebuf2, B, 64, S);
+        ORCA_TRY(tc_extra_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, &E2, mode, s));
         TcMap b0 = rot.next();
-        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB], cur, &E, &b0, 0, s));
+        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB], cur, &E2, &b0, 0, s));
         TcMap b1 = rot.next();
         ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB + 1], b0, nullptr, &b1, 0, s));
         TcMap b2 = rot.next();
@@ -670,6 +710,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       }
       for (int i = 1; i < 28; ++i)
         ORCA_TRY(bottleneck_tc(L + DEC_LCONV + 2 * i, L + DEC_CONV + 2 * i, cur, true, rot, hbuf, s));
+      ORCA_TRY(flush());
       ORCA_TRY(tc_final_head_tmp(cur, L[DEC_FINAL], L[DEC_FINAL + 1], tmp, s));
     }
     ORCA_TRY(symmetrise(tmp, out, B, S, s));
@@ -806,6 +847,11 @@ const char* orca_b200_version(void) { return "orca_b200 0.1 (sm_100a)"; }
 const char* orca_b200_last_error(void) { return t_error.c_str(); }
 uint64_t orca_b200_launch_count(void) { return g_launches.load(); }
 int orca_b200_get_impl(void) { return g_impl.load(); }
+int orca_b200_set_decoder_program(int on) {
+  const int prev = g_dec_program.load();
+  g_dec_program.store(on < 0 ? -1 : (on ? 1 : 0));
+  return prev;
+}
 int orca_b200_set_impl(int impl) {
   if (impl < ORCA_B200_IMPL_AUTO || impl > ORCA_B200_IMPL_TC) { set_error("set_impl: unknown impl %d", impl); return ORCA_B200_EINVAL; }
   g_impl.store(impl);

@@ -57,6 +57,25 @@ int tc_extra_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const fl
                   cudaStream_t s);
 int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp /*[nb][S][S]*/, cudaStream_t s);
 
+// All the 3x3 convs of one decoder call as ONE persistent kernel with grid barriers between layers
+// (conv2d_prog.cu).  add() records a layer, run() uploads the layer table into `scratch` and launches.
+class Tc2dProgram {
+ public:
+  Tc2dProgram();
+  ~Tc2dProgram();
+  Tc2dProgram(const Tc2dProgram&) = delete;
+  Tc2dProgram& operator=(const Tc2dProgram&) = delete;
+  int add(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu);
+  int run(void* scratch, size_t scratch_bytes, cudaStream_t s);
+  int size() const;
+  double flop() const;
+  static size_t scratch_bytes(int max_layers);
+
+ private:
+  struct Impl;
+  Impl* impl;
+};
+
 // glue.cu
 int symmetrise(const float* tmp, float* out, int B, int S, cudaStream_t s);
 

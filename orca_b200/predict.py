@@ -63,10 +63,16 @@ def run_concurrent(jobs, device):
     while len(pool) < len(jobs):
         pool.append(torch.cuda.Stream(device=device))
     results = []
-    for job, st in zip(jobs, pool):
-        st.wait_stream(main)
-        with torch.cuda.stream(st):
-            results.append(job())
+    # one launch per conv while interleaving: the single-kernel decoder program is a cooperative launch that
+    # owns every SM, so two of them would serialise
+    prev = _lib.lib().orca_b200_set_decoder_program(0)
+    try:
+        for job, st in zip(jobs, pool):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                results.append(job())
+    finally:
+        _lib.lib().orca_b200_set_decoder_program(prev)
     for st in pool[:len(jobs)]:
         main.wait_stream(st)
 
