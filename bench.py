@@ -273,7 +273,9 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "bf16x3 (fp32 operands split hi+lo, 3 tcgen05 products, fp32 accumulate)" if args.kernels != "simt" else "f32",
+                "data": "synthetic",
                 "config": {"workload": "H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])",
                            "seq_len": L, "strands": 2, "models": 1, "kernels": args.kernels,
                            "l2": "inputs (512 MB) and stage activations (>1 GB per chunk) exceed the 126 MB L2",
