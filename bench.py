@@ -260,8 +260,14 @@ def main():
         achieved = dom["flop"] / dom["launches"] / (dur_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         split = 3 if key[3] == "tcgen05" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
+        # DRAM bytes per position from the committed ncu --set full capture (profiles/r01_prof_conv1d.md: 1.024 GB read +
+        # 0.978 GB written for 4.224 M positions of the 64->64 kernel = algorithmic 2 x 64 ch x 4 B planes), scaled to
+        # this run's positions per launch
+        traffic = None
+        if key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05":
+            traffic = 474.0 * dom["flop"] / dom["launches"] / (2 * 9 * 64 * 64)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
+                    "traffic": traffic, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
                     "kernel": "%s %d->%d (%s)" % (key[2], key[0], key[1], key[3]),
                     "issued_mma_tflops": achieved * split, "issued_mma_frac": achieved * split / peak,
                     "note": "achieved = ALGORITHMIC conv FLOP (2*positions*c_in*c_out*9) per launch / launch time; the "

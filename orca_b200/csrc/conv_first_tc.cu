@@ -38,7 +38,6 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
-  const long long t0 = (long long)blockIdx.x * 128;
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -50,6 +49,16 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
   }
   for (int i = tid; i < kChunks * 128; i += 128) reinterpret_cast<uint4*>(sBw)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
   if (tid < 64) sBias[tid] = bias[tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // each CTA walks tiles (weights, TMEM allocation and barrier set up once); 3 CTAs per SM overlap each other's phases
+  const int n_tiles = (int)((n + 127) / 128);
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const long long t0 = (long long)tile * 128;
 
   // stage the 148 input positions of the tile (l0-8 .. l0+139; zero outside [0, Ltot)) once, coalesced ...
   __shared__ __align__(16) float sX[148][4];
@@ -86,7 +95,6 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
     }
     __syncwarp();
   }
-  mbar_wait(smem_u32(&bar), 0);
+  mbar_wait(smem_u32(&bar), it & 1);
   tc_fence_after();
   const long long row = t0 + warp * 32 + lane;
 #pragma unroll
@@ -121,6 +129,10 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
         split_store8(v + 8 * ch, out_hi + off, out_lo + off);
       }
     }
+  }
+  tc_fence_before();
+  __syncthreads();  // every warp has drained its TMEM lanes and shared-memory reads before the next tile overwrites them
+  tc_fence_after();
   }
   if (blockIdx.x == 0) {  // pad rows of this sample's planes
     const int tail0 = (int)n + 4, ntail = npad - tail0, per_plane = 4 + ntail;
@@ -242,7 +254,8 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t 
     set_error("tc_lconv1: bad layers / geometry");
     return ORCA_B200_EINVAL;
   }
-  dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb);
+  const long long n_tiles = (n + 127) / 128;
+  dim3 grid((unsigned)(n_tiles < 148 * 3 ? n_tiles : 148 * 3), (unsigned)nb);
   constexpr int kSmem = 3 * kChunks * 128 * 16;
   static bool configured = false;
   if (!configured) {

@@ -45,23 +45,66 @@ class ShardedForward:
         self.b0, self.b1 = shard_bins(self.P, rank, world)
         self.s0, self.s1 = shard_window(L, self.b0, self.b1)
         self.window = None
+        self._copy_stream = None
+        self._ready = None
+        self._cuts = [self.b0, self.b1]
+        self.pieces = 4  # upload pieces overlapped with the forward-strand encoder
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         self.h2d_bytes = 0
         self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
 
     def upload(self, seq_host):
-        """seq_host: (1, L, 4) float32 CPU tensor (pinned for full-speed copies); uploads this rank's window."""
+        """seq_host: (1, L, 4) float32 CPU tensor (pinned for full-speed copies); uploads this rank's window.
+
+        On CUDA the window goes up in `self.pieces` pieces on a copy stream: the forward-strand encoder starts on
+        the first range of bins as soon as piece 1 (those bins + halo) has landed, while the rest is in flight."""
         sl = seq_host[:, self.s0:self.s1, :]
-        self.window = sl.to(self.device, non_blocking=True)
         self.h2d_bytes = sl.numel() * 4
+        self._ready = None
+        if self.device.type != "cuda":
+            self.window = sl.to(self.device)
+            return self.window
+        n = sl.shape[1]
+        npieces = max(1, min(self.pieces, self.b1 - self.b0))
+        self._cuts = [self.b0 + (self.b1 - self.b0) * i // npieces for i in range(npieces + 1)]  # bin boundaries
+        ends = [min(max(c * 4000 + HALO_BP - self.s0, 0), n) for c in self._cuts[1:-1]] + [n]  # window rows per piece
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if self.window is None or self.window.shape[1] != n:
+            self.window = torch.empty((1, n, 4), dtype=torch.float32, device=self.device)
+        cs = self._copy_stream
+        cs.wait_stream(main)  # earlier kernels may still be reading the previous contents
+        events, lo = [], 0
+        with torch.cuda.stream(cs):
+            for hi in ends:
+                if hi > lo:
+                    self.window[:, lo:hi].copy_(sl[:, lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+                lo = max(lo, hi)
+        self._ready = events
         return self.window
 
     def _encode_local(self, reverse):
         """This rank's bins of one strand -> (1, P, 128) buffer (other bins undefined)."""
         enc = torch.empty((1, self.P, 128), dtype=torch.float32, device=self.device)
         bins = (self.P - self.b1, self.P - self.b0) if reverse else (self.b0, self.b1)
-        self.shell.net0(self.window.transpose(1, 2), bin_range=bins, out=enc, reverse_complement=reverse,
-                        window=(self.s0, self.L))
+        kw = dict(out=enc, reverse_complement=reverse, window=(self.s0, self.L))
+        x = self.window.transpose(1, 2)
+        ready, self._ready = (self._ready, None) if not reverse else (None, self._ready)
+        if ready is not None and len(ready) > 1:  # first use after a staged upload (forward strand)
+            main = torch.cuda.current_stream(self.device)
+            for i, ev in enumerate(ready):
+                main.wait_event(ev)
+                self.shell.net0(x, bin_range=(self._cuts[i], self._cuts[i + 1]), **kw)
+        else:
+            pending = ready or self._ready
+            if pending:
+                torch.cuda.current_stream(self.device).wait_event(pending[-1])
+                self._ready = None
+            self.shell.net0(x, bin_range=bins, **kw)
         return enc
 
     def _gather(self, enc, reverse):
