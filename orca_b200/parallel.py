@@ -48,7 +48,7 @@ class ShardedForward:
         self._copy_stream = None
         self._ready = None
         self._cuts = [self.b0, self.b1]
-        self.pieces = 4  # upload pieces overlapped with the forward-strand encoder
+        self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         self.h2d_bytes = 0
         self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
@@ -65,8 +65,10 @@ class ShardedForward:
             self.window = sl.to(self.device)
             return self.window
         n = sl.shape[1]
-        npieces = max(1, min(self.pieces, self.b1 - self.b0))
-        self._cuts = [self.b0 + (self.b1 - self.b0) * i // npieces for i in range(npieces + 1)]  # bin boundaries
+        # a small first piece (the encoder can start after ~1/8 of the upload), then pieces aligned with the
+        # encoder's own chunk boundaries so that no extra halo is recomputed
+        span = self.b1 - self.b0
+        self._cuts = sorted({self.b0 + int(span * f) for f in self.pieces})  # bin boundaries
         ends = [min(max(c * 4000 + HALO_BP - self.s0, 0), n) for c in self._cuts[1:-1]] + [n]  # window rows per piece
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
@@ -136,26 +138,55 @@ class ShardedForward:
                 loc_f, loc_r = self._encode_local(False), self._encode_local(True)
             enc_f, enc_r = self._gather(loc_f, False), self._gather(loc_r, True)
             rev_rank = 1 if world > 1 else 0
-            preds = {}
+            has_1m = hasattr(shell, "denet_1_pt")
+            # where the independent Decoder_1m term of each strand runs: beside the cascades on this GPU (extra
+            # streams) when there are idle ranks none, on ranks 2 / 3 when the box has them
+            x_rank = {False: 2, True: 3} if world >= 4 else {False: 0, True: rev_rank}
+            preds, extras = {}, {}
+            enc_of = {False: enc_f, True: enc_r}
+            nets = {}
 
-            def cascade(reverse, enc):
-                encs = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc)))
-                p, _ = predict.cascade_32mb(shell, encs, 1, mpos, wpos, reverse)
+            def finest(rev):
+                if rev not in nets:
+                    nets[rev] = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc_of[rev])))
+                return nets[rev]
+
+            def cascade(rev):
+                p, _ = predict.cascade_32mb(shell, finest(rev), 1, mpos, wpos, rev, inline_1m=False)
                 return torch.cat([t[0] for t in p], 0)  # (6, 250, 250)
 
-            mine = [(rev, enc) for rev, owner, enc in ((False, 0, enc_f), (True, rev_rank, enc_r)) if rank == owner]
-            # independent strand cascades on separate CUDA streams: each decoder conv is a ~20 us launch whose
-            # prologue/tail latency the other stream's kernels fill
-            outs = predict.run_concurrent([lambda r=r, e=e: cascade(r, e) for r, e in mine], self.device)
-            for (rev, _), o in zip(mine, outs):
-                preds[rev] = o
-            if world > 1:
-                if rank == rev_rank:
-                    dist.send(preds[True], dst=0)
-                elif rank == 0:
-                    buf = torch.empty((6, 250, 250), dtype=torch.float32, device=self.device)
-                    dist.recv(buf, src=rev_rank)
-                    preds[True] = buf
+            jobs = []
+            for rev, owner in ((False, 0), (True, rev_rank)):
+                if rank == owner:
+                    finest(rev)  # Encoder2 once, on the main stream, before the concurrent jobs read it
+                    jobs.append(("c", rev))
+                if has_1m and rank == x_rank[rev]:
+                    finest(rev)
+                    jobs.append(("x", rev))
+            # independent chains on separate CUDA streams: each decoder conv is a ~20 us launch whose prologue/tail
+            # latency the other streams' kernels fill (a single chain runs as one persistent program kernel instead)
+            outs = predict.run_concurrent(
+                [(lambda r=r: cascade(r)) if kind == "c" else (lambda r=r: predict.level1_extra(shell, finest(r), mpos, wpos, r)[0, 0])
+                 for kind, r in jobs], self.device)
+            for (kind, rev), o in zip(jobs, outs):
+                (preds if kind == "c" else extras)[rev] = o
+            if world > 1:  # collect on rank 0: the reverse cascade, and the Decoder_1m terms computed elsewhere
+                def move(t_dict, rev, src, shape):
+                    if src == 0:
+                        return
+                    if rank == src:
+                        dist.send(t_dict[rev].contiguous(), dst=0)
+                    elif rank == 0:
+                        buf = torch.empty(shape, dtype=torch.float32, device=self.device)
+                        dist.recv(buf, src=src)
+                        t_dict[rev] = buf
+                move(preds, True, rev_rank, (6, 250, 250))
+                if has_1m:
+                    move(extras, False, x_rank[False], (250, 250))
+                    move(extras, True, x_rank[True], (250, 250))
             if rank != 0:
                 return None
+            if has_1m:
+                for rev in (False, True):
+                    preds[rev][5] += extras[rev]
             return 0.5 * preds[False] + 0.5 * torch.flip(preds[True], [1, 2])

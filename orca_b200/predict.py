@@ -94,8 +94,30 @@ def encode_strand(model, seq_dev, reverse):
     return model.net0(seq_dev.transpose(1, 2), reverse_complement=reverse)
 
 
-def cascade_32mb(model, encodings, batch, mpos, wpos, reverse):
-    """Decoder cascade 32 -> 1 Mb of one (model, strand) (orca_predict.py:348-500)."""
+def cascade_starts_32mb(mpos, wpos, reverse):
+    """Start bins of the six zoom levels: host integer arithmetic only (orca_predict.py:470-499)."""
+    starts = [0]
+    for j, level in enumerate([32, 16, 8, 4, 2, 1]):
+        if not reverse:
+            si = int(np.clip(np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + starts[j] * 4000))
+                                      / (4000 * level)), 0, 125))
+        else:
+            si = int(np.clip(np.ceil(((wpos + 16000000 - starts[j] * 4000) - (mpos + level * 1000000 / 4))
+                                     / (4000 * level)), 0, 125))
+        starts.append(starts[j] + si * level)
+    return starts[:-1]
+
+
+def level1_extra(model, encodings, mpos, wpos, reverse):
+    """Decoder_1m term of the 1 Mb level (orca_predict.py:362-366).  It depends only on the level-1 encoding and
+    the (host-computed) start bin, so it can run beside the cascade -- on another stream or another rank."""
+    s = int(cascade_starts_32mb(mpos, wpos, reverse)[5])
+    return model.denet_1_pt.forward(encodings[1][:, :, s:s + 250])
+
+
+def cascade_32mb(model, encodings, batch, mpos, wpos, reverse, inline_1m=True):
+    """Decoder cascade 32 -> 1 Mb of one (model, strand) (orca_predict.py:348-500).  With inline_1m=False the
+    caller adds level1_extra(...) to the last map itself."""
     device = encodings[1].device
     preds, starts = [], [0]
     start_index = 0
@@ -105,7 +127,7 @@ def cascade_32mb(model, encodings, batch, mpos, wpos, reverse):
         xl = encodings[level][:, :, s:s + 250]
         coarse = None if j == 0 else preds[j - 1][:, :, start_index:start_index + 125, start_index:start_index + 125]
         pred = model.denets[level].forward(xl, distenc, coarse)
-        if level == 1 and j > 0 and hasattr(model, "denet_1_pt"):
+        if level == 1 and j > 0 and hasattr(model, "denet_1_pt") and inline_1m:
             pred = pred + model.denet_1_pt.forward(xl)
         if not reverse:
             start_index = int(np.clip(np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + starts[j] * 4000))
