@@ -378,7 +378,10 @@ int Tc2dProgram::run(void* scratch, size_t scratch_bytes_, cudaStream_t s) {
   ORCA_CUDA_OK(cudaMemsetAsync(counter, 0, 256, s));
   ORCA_CUDA_OK(cudaMemcpyAsync(d_layers, impl->layers.data(), (size_t)n * sizeof(Tc2dLayer), cudaMemcpyHostToDevice, s));
   const int smem = g.oper_bytes + 64 * 4 + (2 * kMaxNA + 2 * kMaxNW + 4) * 8 + 16 + 128;
-  static bool configured = false;
+  static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 31];
   static int sms = 148;
   if (!configured) {
     ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

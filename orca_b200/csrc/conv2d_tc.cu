@@ -437,7 +437,10 @@ int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out,
   const int sms = sm_count2();
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
   if (a.total_tiles <= 0) return ORCA_B200_OK;
-  static bool configured = false;
+  static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 31];
   if (!configured) {
     ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ORCA_CUDA_OK(cudaFuncSetAttribute(conv2d_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

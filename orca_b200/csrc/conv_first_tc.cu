@@ -257,7 +257,10 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t 
   const long long n_tiles = (n + 127) / 128;
   dim3 grid((unsigned)(n_tiles < 148 * 3 ? n_tiles : 148 * 3), (unsigned)nb);
   constexpr int kSmem = 3 * kChunks * 128 * 16;
-  static bool configured = false;
+  static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 31];
   if (!configured) {
     ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;

@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
 template <int C_IN, int C_OUT, bool CONCAT>
 int launch_tc_impl(const TcKArgs& a, int sms, cudaStream_t s) {
   using Cfg = TcCfg<C_IN, C_OUT>;
-  static bool configured = false;  // per instantiation
+  static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_dev[cur_dev & 31];
   if (!configured) {
     ORCA_CUDA_OK(cudaFuncSetAttribute(conv1d_tc_kernel<C_IN, C_OUT, CONCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
