@@ -76,10 +76,12 @@ __device__ __forceinline__ void tile_coords(const Tc2dGeom& g, int tile, int& b,
 }
 
 // ---- producer: bulk copies of A runs and weight stages for one layer ----------------------------------
-__device__ __forceinline__ void producer_layer(const Tc2dLayer& L, const Tc2dGeom& g, uint32_t sA, uint32_t sW, const Bars& B) {
+// `preloaded`: the layer's resident weight stages were already requested at the previous layer boundary
+__device__ __forceinline__ void producer_layer(const Tc2dLayer& L, const Tc2dGeom& g, uint32_t sA, uint32_t sW, const Bars& B,
+                                               bool preloaded) {
   const int nkb = (L.c_in + 63) / 64, R = 128 + 2 * L.d, kc = (L.c_in < 64 ? L.c_in : 64) / 8;
   const uint32_t aLoOff = (uint32_t)kc * R * 16, tapBytes = 2u * kc * L.c_out * 16;
-  uint32_t a_it = 0, w_it = 0, loaded = 0;
+  uint32_t a_it = 0, w_it = 0, loaded = (preloaded && L.resident) ? 0xFFFFFFFFu : 0u;
   for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
     int b, y, x0;
     tile_coords(g, tile, b, y, x0);
@@ -122,11 +124,15 @@ __device__ __forceinline__ void producer_layer(const Tc2dLayer& L, const Tc2dGeo
 // ---- MMA issuer for one layer ---------------------------------------------------------------------------
 template <int C_OUT, int KSTEPS>
 __device__ __forceinline__ void mma_layer(const Tc2dLayer& L, const Tc2dGeom& g, uint32_t sA, uint32_t sW, const Bars& B,
-                                          uint32_t tmem, uint32_t& acc_it) {
+                                          uint32_t tmem, uint32_t& acc_it, bool preloaded) {
   const int nkb = (L.c_in + 63) / 64, R = 128 + 2 * L.d, kc = (L.c_in < 64 ? L.c_in : 64) / 8;
   const uint32_t aLoOff = (uint32_t)kc * R * 16, tapBytes = 2u * kc * C_OUT * 16;
   const uint32_t aStep = (uint32_t)(2 * R * 16) >> 4, aLoStep = aLoOff >> 4, tapStep = tapBytes >> 4;
   uint32_t a_it = 0, w_it = 0, waited = 0;
+  if (preloaded && L.resident) {  // every preloaded stage must have landed before this layer's barriers are re-initialised
+    for (int sid = 0; sid < 3 * nkb; ++sid) mbar_wait(B.w_full + 8 * sid, 0);
+    waited = 0xFFFFFFFFu;
+  }
   for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
     int b, y, x0;
     tile_coords(g, tile, b, y, x0);
@@ -272,11 +278,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv2d_program_kernel(const Tc2d
     const uint32_t sA = smem_u32(smem), sW = sA + (uint32_t)L.NA * L.a_slot_bytes;
     const int variant = L.c_out == 32 ? 0 : (L.c_in == 32 ? 2 : 1);  // (32,4) (64,4) (64,2)
     if (warp == 0) {
-      producer_layer(L, g, sA, sW, B);
+      producer_layer(L, g, sA, sW, B, l > 0);
     } else if (warp == 1) {
-      if (variant == 0) mma_layer<32, 4>(L, g, sA, sW, B, tmem, acc_it);
-      else if (variant == 1) mma_layer<64, 4>(L, g, sA, sW, B, tmem, acc_it);
-      else mma_layer<64, 2>(L, g, sA, sW, B, tmem, acc_it);
+      if (variant == 0) mma_layer<32, 4>(L, g, sA, sW, B, tmem, acc_it, l > 0);
+      else if (variant == 1) mma_layer<64, 4>(L, g, sA, sW, B, tmem, acc_it, l > 0);
+      else mma_layer<64, 2>(L, g, sA, sW, B, tmem, acc_it, l > 0);
     } else {
       if (variant == 0) epilogue_layer<32>(L, g, B, tmem, sBias, acc_it, warp, lane);
       else epilogue_layer<64>(L, g, B, tmem, sBias, acc_it, warp, lane);
@@ -289,6 +295,20 @@ __global__ void __launch_bounds__(kThreadsP, 1) conv2d_program_kernel(const Tc2d
       atomicAdd(counter, 1u);
       init_rings();                          // A/W rings restart from phase 0 for the next layer's carve
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      {
+        // This CTA's shared memory is idle now (all its MMAs have completed), and weights do not depend on the
+        // other CTAs: fetch the next layer's resident weight stages while waiting at the grid barrier.
+        const Tc2dLayer& N = layers[l + 1];
+        if (N.resident) {
+          const int nkbN = (N.c_in + 63) / 64, kcN = (N.c_in < 64 ? N.c_in : 64) / 8;
+          const uint32_t stageN = 3u * 2u * kcN * N.c_out * 16;
+          const uint32_t sWN = smem_u32(smem) + (uint32_t)N.NA * N.a_slot_bytes;
+          for (int sid = 0; sid < 3 * nkbN; ++sid) {
+            mbar_expect_tx(B.w_full + 8 * sid, stageN);
+            bulk_g2s(sWN + sid * N.w_stage_bytes, N.w + (size_t)sid * stageN, stageN, B.w_full + 8 * sid);
+          }
+        }
+      }
       const unsigned int target = (unsigned int)(l + 1) * gridDim.x;
       while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(64);
       __threadfence();
