@@ -238,3 +238,20 @@ def test_encoder_locality_at_scale():
                 ref = oracle.encoder_run(sd, torch.from_numpy(s[:, lo:hi]).transpose(1, 2))
             ref = ref[:, :, b0 - lo // 4000: b0 - lo // 4000 + 10]
             assert relerr(full[:, :, b0:b0 + 10].numpy(), ref.numpy()) <= TOL, (rc, b0)
+
+
+def test_two_models_concurrent_cascades_are_consistent():
+    """Default genomepredict runs two models x two strands = four independent cascades, interleaved on four
+    CUDA streams here; every model's maps must equal its single-model run exactly (no cross-stream races)."""
+    from orca_b200 import models, predict
+    a, b = models.H1esc(seed=7), models.Hff(seed=9)
+    seq = synthetic.random_sequence(1, 32_000_000, 105)
+    mpos, wpos = 16_500_000, 16_000_000
+    both = predict.genomepredict(seq, "chrS", mpos, wpos, models=[a, b])
+    only_a = predict.genomepredict(seq, "chrS", mpos, wpos, models=[a])
+    only_b = predict.genomepredict(seq, "chrS", mpos, wpos, models=[b])
+    for i in range(6):
+        assert np.array_equal(both["predictions"][0][i], only_a["predictions"][0][i]), i
+        assert np.array_equal(both["predictions"][1][i], only_b["predictions"][0][i]), i
+    g = gold("genomepredict_32mb")
+    assert max(relerr(p, r) for p, r in zip(both["predictions"][0], g["predictions"])) <= TOL
