@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--seq-len", type=int, default=SEQ_LEN)
+    ap.add_argument("--workload", default="32mb", choices=["32mb", "256mb"],
+                    help="32mb = BASELINE configs[1] (default, what the driver runs); 256mb = configs[3], the "
+                         "H1esc_256M-like genomepredict_256Mb forward (256 Mb, 4 levels), sequence-sharded the same way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk-bp", type=int, default=0, help="encoder chunk length in bp (0 = library default)")
     ap.add_argument("--concurrent-strands", action="store_true", help="encode the two strands on two CUDA streams")
@@ -186,15 +189,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_impl(args.kernels)
     peaks = load_peaks()
-    L = args.seq_len
+    big = args.workload == "256mb"
+    L = 256_000_000 if big else args.seq_len
+    maps_per_step = 8 if big else MAPS_PER_STEP
+    flop_per_strand = 120.6e12 if big else FLOP_PER_STRAND * (L / SEQ_LEN)
+    workload = ("H1esc_256M-like 256 Mb multiscale forward (genomepredict_256Mb), batch 1 (BASELINE configs[3])" if big
+                else "H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])")
 
-    shell = models.H1esc(seed=0, device=dev)
+    shell = (models.H1esc_256M if big else models.H1esc)(seed=0, device=dev)
     shell.net0.chunk_bp = args.chunk_bp
     seq_host = torch.from_numpy(synthetic.random_sequence(1, L, 0)).pin_memory()
     runner = parallel.ShardedForward(shell, L, rank, world, dev)
     runner.concurrent_strands = args.concurrent_strands
     runner.upload(seq_host)  # device-resident input for the `value` leg
-    mpos = wpos = L // 2
+    if big:
+        runner.set_background(synthetic.normmat_256mb(chrlen_bins=7500), 7500 * 32000)
+        runner.d2h_bytes = 4 * 250 * 250 * 4 if rank == 0 else 0
+        mpos, wpos = 100_000_000, 128_000_000
+    else:
+        mpos = wpos = L // 2
 
     def barrier():
         if world > 1:
@@ -282,13 +295,13 @@ def main():
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "bf16x3 (fp32 operands split hi+lo, 3 tcgen05 products, fp32 accumulate)" if args.kernels != "simt" else "f32",
                 "data": "synthetic",
-                "config": {"workload": "H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])",
+                "config": {"workload": workload,
                            "seq_len": L, "strands": 2, "models": 1, "kernels": args.kernels,
                            "l2": "inputs (512 MB) and stage activations (>1 GB per chunk) exceed the 126 MB L2",
                            "parallelism": "sequence-sharded encoder x%d + all-gather, strand-parallel cascades" % world
                            if world > 1 else "single GPU"},
-                "contact_maps_per_s": MAPS_PER_STEP / (ms_step * 1e-3),
-                "algorithmic_tflops": 2 * FLOP_PER_STRAND * (L / SEQ_LEN) / (ms_step * 1e-3) / 1e12,
+                "contact_maps_per_s": maps_per_step / (ms_step * 1e-3),
+                "algorithmic_tflops": 2 * flop_per_strand / (ms_step * 1e-3) / 1e12,
                 "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(runner.h2d_bytes), "d2h_bytes_per_step": int(runner.d2h_bytes)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
@@ -298,12 +311,13 @@ def main():
             one()
             t0 = time.perf_counter()
             tb, te, td, tm = one()
-            full = cpu_extrapolate(tb, te, td, tm)
+            # 256 Mb: 320 blocks, pooling half of Encoder2 at 64000 bins (8 x 1/3 of the timed 8000-bin U-net), 4 decoders
+            full = 2 * (320 * tb + 8 * te / 3 + 4 * td) if big else cpu_extrapolate(tb, te, td, tm)
             line["cpu_baseline"] = {
-                "value": 2 * SEQ_LEN / full / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
+                "value": 2 * L / full / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
                 "sample": "1 of 40 encoder blocks (912 kb incl. halo), Encoder2@8000, 1 Decoder, 1 Decoder_1m; "
                           "extrapolated to the full 2-strand step", "sample_wall_s": time.perf_counter() - t0,
-                "maps_per_s": MAPS_PER_STEP / full}
+                "maps_per_s": maps_per_step / full}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

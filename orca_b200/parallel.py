@@ -34,7 +34,8 @@ def shard_window(L, b0, b1):
 
 
 class ShardedForward:
-    """32 Mb genomepredict-equivalent forward of one shell, sequence-sharded over `world` ranks."""
+    """genomepredict-equivalent forward of one shell, sequence-sharded over `world` ranks: the 32 Mb shells
+    (6 maps, 32 -> 1 Mb) and the 256 Mb shells (4 maps, 256 -> 32 Mb; call set_background first)."""
 
     def __init__(self, shell, L, rank=0, world=1, device=None):
         self.shell, self.L, self.rank, self.world = shell, L, rank, world
@@ -45,6 +46,7 @@ class ShardedForward:
         self.b0, self.b1 = shard_bins(self.P, rank, world)
         self.s0, self.s1 = shard_window(L, self.b0, self.b1)
         self.window = None
+        self.background, self.chrlen = None, None
         self._copy_stream = None
         self._ready = None
         self._cuts = [self.b0, self.b1]
@@ -52,6 +54,12 @@ class ShardedForward:
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         self.h2d_bytes = 0
         self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
+
+    def set_background(self, normmat, chrlen):
+        """256 Mb shells: the caller's (8000, 8000) background matrix at 32 kb bins (as passed to
+        genomepredict_256Mb) and the chromosome length; uploaded once per rank that runs a cascade."""
+        self.background = predict.prepare_background(normmat, self.device) if self.rank <= 1 else None
+        self.chrlen = chrlen
 
     def upload(self, seq_host):
         """seq_host: (1, L, 4) float32 CPU tensor (pinned for full-speed copies); uploads this rank's window.
@@ -146,14 +154,26 @@ class ShardedForward:
             enc_of = {False: enc_f, True: enc_r}
             nets = {}
 
+            is256 = str(getattr(shell, "kind", "")).endswith("256m")
+            n_maps = 4 if is256 else 6
+
             def finest(rev):
                 if rev not in nets:
-                    nets[rev] = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc_of[rev])))
+                    if is256:  # net(net1(net0(x))[-1])  (orca_predict.py:675-683); only the pooling half of net1 is needed
+                        e128 = shell.net1(enc_of[rev], coarsest_only=True)[-1]
+                        nets[rev] = dict(zip([32, 64, 128, 256], shell.net(e128)))
+                    else:
+                        nets[rev] = dict(zip([1, 2, 4, 8, 16, 32], shell.net(enc_of[rev])))
                 return nets[rev]
 
             def cascade(rev):
-                p, _ = predict.cascade_32mb(shell, finest(rev), 1, mpos, wpos, rev, inline_1m=False)
-                return torch.cat([t[0] for t in p], 0)  # (6, 250, 250)
+                if is256:
+                    if self.background is None:
+                        raise RuntimeError("256 Mb shells need set_background(normmat, chrlen) before forward()")
+                    p = predict.cascade_256mb(shell, finest(rev), 1, self.background, self.chrlen, mpos, wpos, rev)[0]
+                else:
+                    p, _ = predict.cascade_32mb(shell, finest(rev), 1, mpos, wpos, rev, inline_1m=False)
+                return torch.cat([t[0] for t in p], 0)  # (n_maps, 250, 250)
 
             jobs = []
             for rev, owner in ((False, 0), (True, rev_rank)):
@@ -180,7 +200,7 @@ class ShardedForward:
                         buf = torch.empty(shape, dtype=torch.float32, device=self.device)
                         dist.recv(buf, src=src)
                         t_dict[rev] = buf
-                move(preds, True, rev_rank, (6, 250, 250))
+                move(preds, True, rev_rank, (n_maps, 250, 250))
                 if has_1m:
                     move(extras, False, x_rank[False], (250, 250))
                     move(extras, True, x_rank[True], (250, 250))

@@ -190,6 +190,15 @@ def genomepredict(sequence, mchr, mpos=-1, wpos=-1, models=(), targets=None, ann
     return output
 
 
+def prepare_background(normmat, device):
+    """Caller's (n, n) float64 background matrix -> device, NaNs replaced by the minimum (orca_predict.py:668-671)."""
+    t = torch.as_tensor(np.asarray(normmat, dtype=np.float64)).to(device)
+    nan = torch.isnan(t)
+    if bool(nan.any()):
+        t = torch.where(nan, t[~nan].min(), t)
+    return t
+
+
 def background_level(normmat_dev, r0, f, flip=False, size=250):
     """log(block-nanmean) of an (n, n) float64 device matrix -> (1, 1, size, size) float32."""
     out = torch.empty((1, 1, size, size), dtype=torch.float32, device=normmat_dev.device)
@@ -241,13 +250,7 @@ def genomepredict_256Mb(sequence, mchr, normmats, chrlen, mpos=-1, wpos=-1, mode
     with torch.no_grad(), torch.cuda.device(device):
         seq_dev = _to_device_sequence(sequence, device)
         B = seq_dev.shape[0]
-        nm_dev = []
-        for nm in normmats:  # NaN fill with the minimum (orca_predict.py:668-671), once, on the device
-            t = torch.as_tensor(np.asarray(nm, dtype=np.float64)).to(device)
-            nan = torch.isnan(t)
-            if bool(nan.any()):
-                t = torch.where(nan, t[~nan].min(), t)
-            nm_dev.append(t)
+        nm_dev = [prepare_background(nm, device) for nm in normmats]
         per_strand, allns, starts0 = [], [], None
         for reverse in (False, True):
             for ii, model in enumerate(models):

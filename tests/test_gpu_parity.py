@@ -255,3 +255,22 @@ def test_two_models_concurrent_cascades_are_consistent():
         assert np.array_equal(both["predictions"][1][i], only_b["predictions"][0][i]), i
     g = gold("genomepredict_32mb")
     assert max(relerr(p, r) for p, r in zip(both["predictions"][0], g["predictions"])) <= TOL
+
+
+def test_sharded_runner_256mb_matches_driver():
+    """The sharded runner on a 256 Mb shell (world size 1) is the same computation as
+    predict.genomepredict_256Mb: a full-size 256 Mb pass (320 reference blocks' worth of sequence)."""
+    from orca_b200 import models, parallel, predict
+    shell = models.H1esc_256M(seed=3)
+    L = 256_000_000
+    seq = synthetic.random_sequence(1, L, 21)
+    nm = synthetic.normmat_256mb(chrlen_bins=7500)
+    mpos, wpos, chrlen = 100_000_000, 128_000_000, 7500 * 32000
+    ref = predict.genomepredict_256Mb(seq, "chrS", [nm], chrlen, mpos, wpos, models=[shell])
+    runner = parallel.ShardedForward(shell, L, 0, 1, torch.device("cuda"))
+    runner.set_background(nm, chrlen)
+    runner.upload(torch.from_numpy(seq))
+    maps = runner.forward(mpos, wpos).cpu().numpy()
+    assert maps.shape == (4, 250, 250) and np.isfinite(maps).all()
+    for i in range(4):
+        assert relerr(maps[i], ref["predictions"][0][i]) <= 1e-6, i
