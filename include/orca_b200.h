@@ -55,6 +55,12 @@ enum {
   ORCA_B200_DECODER_1M = 6, /* Decoder_1m orca_modules.py:491-800   (78 convs) */
   ORCA_B200_NET = 7         /* Net        orca_modules.py:1409-1900 (106 convs [+2 final_1d]) */
 };
+/*
+ * Decoder / Decoder_1m / Net also cover the multi-map variants of orca_leukemia.py (Decoder(num_2d) :512-993,
+ * Decoder_1m(num_2d) :996-1315, Net(num_2d, num_1d) :16-509: the same trees with `final` 64 -> max(num_2d,5) ->
+ * num_2d and combiner inputs of 64+num_2d / 128+num_2d channels).  num_2d (1..8) is read off the module's own
+ * final 1x1 convolution at creation; every tensor documented below as (B, 1, ...) is then (B, num_2d, ...).
+ */
 
 /* flags for orca_b200_module_create */
 #define ORCA_B200_UPSAMPLE_NEAREST 0u  /* Decoder(upsample_mode='nearest')  */
@@ -124,6 +130,7 @@ int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_
                             uint32_t flags, int32_t num_1d, orca_b200_module** out);
 void orca_b200_module_destroy(orca_b200_module* m);
 int orca_b200_module_kind(const orca_b200_module* m);
+int orca_b200_module_num_2d(const orca_b200_module* m); /* output maps per sample (1 for orca_modules) */
 
 /*
  * Encoder.forward.  x: (B, 4, L) with element strides (sB, sC, sL) -- genomepredict hands
@@ -161,18 +168,18 @@ int orca_b200_encoder2_forward(const orca_b200_module* m, const float* x, int64_
                                size_t workspace_bytes, void* stream);
 
 /*
- * Decoder.forward(x, distenc, y) and Decoder_1m.forward(x).
+ * Decoder.forward(x, distenc, y) and Decoder_1m.forward(x).          C = num_2d of the module (1 in orca_modules)
  *   x       (B, 128, S), element strides (xsB, xsC, xsL)           S = 250 in Orca
- *   distenc (B, 1, S, S), strides (dsB, dsH, dsW) [dsB may be 0: expanded view]; Decoder only
- *   y       (B, 1, S/2, S/2), strides (ysB, ysH, ysW) or NULL; Decoder only
- *   out     (B, 1, S, S) contiguous
+ *   distenc (B, C, S, S), strides (dsB, dsC, dsH, dsW) [dsB may be 0: expanded view]; Decoder only
+ *   y       (B, C, S/2, S/2), strides (ysB, ysC, ysH, ysW) or NULL; Decoder only
+ *   out     (B, C, S, S) contiguous
  */
 size_t orca_b200_decoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t S);
 int orca_b200_decoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t S,
                               int64_t xsB, int64_t xsC, int64_t xsL, const float* distenc,
-                              int64_t dsB, int64_t dsH, int64_t dsW, const float* y, int64_t ysB,
-                              int64_t ysH, int64_t ysW, float* out, void* workspace,
-                              size_t workspace_bytes, void* stream);
+                              int64_t dsB, int64_t dsC, int64_t dsH, int64_t dsW, const float* y,
+                              int64_t ysB, int64_t ysC, int64_t ysH, int64_t ysW, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Net.forward (Orca-1Mb).  x as for the encoder; L/4000 is the map size S.

@@ -50,6 +50,19 @@ def import_reference():
     return orca_modules, orca_predict
 
 
+def import_reference_leukemia():
+    """The network classes of the unmodified /root/reference/orca_leukemia.py (Net, Decoder, Decoder_1m, Encoder,
+    Encoder2; :16-1601).  The file cannot be imported whole: its last two lines instantiate OrcaLeukemiaA/B, which
+    load Zenodo resources and call .cuda() (:1872-1873).  So the source is read from the reference tree at run time
+    and only the part before `class OrcaLeukemiaA` is executed (nothing is copied into this repository)."""
+    os.environ.setdefault("ORCA_PATH", REF)
+    src = open(os.path.join(REF, "orca_leukemia.py")).read()
+    head = src[:src.index("class OrcaLeukemiaA")]
+    mod = types.ModuleType("orca_leukemia_classes")
+    exec(compile(head, os.path.join(REF, "orca_leukemia.py"), "exec"), mod.__dict__)
+    return mod
+
+
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
@@ -142,6 +155,50 @@ def main():
             assert relerr(yo, y) < 2e-6
             save(name, weight_seed=16, S=S, B=B, x_seed=303, out=y)
 
+        # ---------------- multi-map variants (orca_leukemia.py; num_2d = 2 / 6) ----------------
+        ol = import_reference_leukemia()
+        for name, n2d, S, B, coarse in [("leukemia_decoder_n2_64", 2, 64, 2, True), ("leukemia_decoder_n6_48", 6, 48, 1, True),
+                                        ("leukemia_decoder_n6_30_nocoarse", 6, 30, 2, False),
+                                        ("leukemia_decoder_n2_250", 2, 250, 1, True)]:
+            if not want(name):
+                continue
+            m = ref_module(ol.Decoder, 31, n2d)
+            x = randn((B, 128, S), 311, 0.5)
+            distenc = randn((1, n2d, S, S), 312).expand(B, -1, -1, -1)
+            yc = randn((B, n2d, S // 2, S // 2), 313) if coarse else None
+            y = m(x, distenc, yc).numpy()
+            yo = oracle.decoder_forward(m.state_dict(), x, distenc, yc, "nearest").numpy()
+            print(name, y.shape, "oracle relerr %.2e" % relerr(yo, y), "absmax %.3f" % np.abs(y).max())
+            assert relerr(yo, y) < 2e-6
+            save(name, weight_seed=31, num_2d=n2d, S=S, B=B, coarse=coarse, x_seed=311, d_seed=312, y_seed=313, out=y)
+        if want("leukemia_decoder1m_n2_40"):
+            m = ref_module(ol.Decoder_1m, 32, 2)
+            x = randn((2, 128, 40), 314, 0.5)
+            y = m(x).numpy()
+            yo = oracle.decoder_1m_forward(m.state_dict(), x).numpy()
+            print("leukemia_decoder1m_n2_40", y.shape, "oracle relerr %.2e" % relerr(yo, y))
+            assert relerr(yo, y) < 2e-6
+            save("leukemia_decoder1m_n2_40", weight_seed=32, num_2d=2, S=40, B=2, x_seed=314, out=y)
+        if want("leukemia_net_n6_24k"):
+            m = ref_module(ol.Net, 33, 6, 8)
+            x = torch.from_numpy(synthetic.random_sequence(1, 24000, 108, 0.01)).transpose(1, 2)
+            pred, p1d = m(x)
+            po, p1o = oracle.net_forward(m.state_dict(), x, num_1d=8)
+            print("leukemia_net_n6_24k", pred.shape, p1d.shape, "oracle relerr %.2e %.2e" % (relerr(po.numpy(), pred.numpy()), relerr(p1o.numpy(), p1d.numpy())))
+            assert relerr(po.numpy(), pred.numpy()) < 2e-6 and relerr(p1o.numpy(), p1d.numpy()) < 2e-6
+            save("leukemia_net_n6_24k", weight_seed=33, num_2d=6, num_1d=8, L=24000, B=1, seq_seed=108, n_fraction=0.01,
+                 out=pred.numpy(), out_1d=p1d.numpy())
+        if want("state_dict_keys_leukemia"):
+            import json
+            keys = {}
+            for tag, ctor in [("Decoder2", lambda: ol.Decoder(2)), ("Decoder6", lambda: ol.Decoder(6)),
+                              ("Decoder_1m2", lambda: ol.Decoder_1m(2)), ("Net6_8", lambda: ol.Net(6, 8)),
+                              ("Encoder", ol.Encoder), ("Encoder2", ol.Encoder2)]:
+                keys[tag] = [[k, list(v.shape)] for k, v in ctor().state_dict().items()]
+            with open(os.path.join(GOLD, "state_dict_keys_leukemia.json"), "w") as f:
+                json.dump(keys, f)
+            print("  wrote state_dict_keys_leukemia.json")
+
         # ---------------- Net ----------------
         if want("net_48k"):
             m = ref_module(om.Net, 17, num_1d=32)
@@ -178,6 +235,19 @@ def main():
             preds = np.stack(res["predictions"][0]).astype(np.float32)
             print("genomepredict_32mb", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
             save("genomepredict_32mb", shell_seed=7, seq_seed=105, mpos=mpos, wpos=wpos, predictions=preds,
+                 start_coords=np.asarray(res["start_coords"], dtype=np.int64))
+
+        if want("genomepredict_32mb_leukemia") and args.big:
+            # OrcaLeukemiaA-like shell (2 datasets: (2,250,250) normmats, pooling-only Encoder2, nearest upsample)
+            # through the unmodified genomepredict
+            t0 = time.time()
+            shell = models.build_shell(ol, "leukemia_a", seed=9)
+            seq = synthetic.random_sequence(1, 32000000, 109)
+            mpos, wpos = 15200000, 16000000
+            res = op.genomepredict(seq, "chrS", mpos, wpos, models=[shell], use_cuda=False)
+            preds = np.stack(res["predictions"][0]).astype(np.float32)
+            print("genomepredict_32mb_leukemia", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
+            save("genomepredict_32mb_leukemia", shell_seed=9, seq_seed=109, mpos=mpos, wpos=wpos, predictions=preds,
                  start_coords=np.asarray(res["start_coords"], dtype=np.int64))
 
         if want("genomepredict_256mb_stub"):

@@ -41,6 +41,7 @@ SIGNATURES = {
                                                ctypes.c_uint32, ctypes.c_int32, ctypes.POINTER(_vp)]),
     "orca_b200_module_destroy": (None, [_vp]),
     "orca_b200_module_kind": (ctypes.c_int, [_vp]),
+    "orca_b200_module_num_2d": (ctypes.c_int, [_vp]),
     "orca_b200_encoder_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64, _i64]),
     "orca_b200_encoder_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64,
                                                  _i64, _vp, ctypes.c_size_t, _vp]),
@@ -48,8 +49,8 @@ SIGNATURES = {
     "orca_b200_encoder2_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(_vp),
                                                   ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_size_t, _vp]),
     "orca_b200_decoder_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64]),
-    "orca_b200_decoder_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
-                                                 _vp, _i64, _i64, _i64, _vp, _vp, ctypes.c_size_t, _vp]),
+    "orca_b200_decoder_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64,
+                                                 _vp, _i64, _i64, _i64, _i64, _vp, _vp, ctypes.c_size_t, _vp]),
     "orca_b200_net_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64]),
     "orca_b200_net_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
                                              ctypes.c_size_t, _vp]),

@@ -50,8 +50,10 @@ struct ConvLayer {
   // tensor-core images (bf16 hi/lo split, UMMA-swizzled), optional
   void* tc_w = nullptr;
   size_t tc_w_bytes = 0;
-  // odd extra input channel (129th / 65th channel of the Decoder combiners): w_extra[tap][c_out]
+  // extra input channels of the Decoder combiners (the 129th / 65th channel in orca_modules, num_2d of them in
+  // orca_leukemia), kept out of the aligned implicit GEMM: w_extra[n_extra][tap][c_out]
   float* w_extra = nullptr;
+  int n_extra = 0;
   // bias that goes with tc_w when it differs from b (the composed lconv1 of the Encoder, conv_first_tc.cu)
   float* tc_bias = nullptr;
 };
@@ -88,12 +90,14 @@ int to_channel_last(const float* x, int64_t sB, int64_t sC, int64_t sL, float* o
                     int64_t L, cudaStream_t s);
 // mat[b][i][j][c] = xcl[b][i][c] + xcl[b][j][c]   (xcl channel-last [B][S][C])
 int outer_sum(const float* xcl, float* mat, int B, int C, int S, cudaStream_t s);
-// single-channel 3x3 conv feeding c_out channels (the odd extra input channel of the
-// Decoder combiners).  mode 0: src is (B,1,S,S); mode 1/2: src is (B,1,S/2,S/2) and is
-// upsampled x2 on the fly (1 = nearest, 2 = bilinear align_corners=False).
-int extra_channel_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra,
-                       float* out, int B, int S, int c_out, int mode, cudaStream_t s);
-// final head: tmp[b][i][j] = w2 . relu(W1 v + b1) + b2 ; out = 0.5*(tmp + tmp^T)
+// n_extra-channel 3x3 conv feeding c_out channels (the extra input channels of the Decoder
+// combiners: 1 in orca_modules, num_2d in orca_leukemia).  mode 0: src is (B,n_extra,S,S);
+// mode 1/2: src is (B,n_extra,S/2,S/2) and is upsampled x2 on the fly (1 = nearest,
+// 2 = bilinear align_corners=False).  w_extra is [n_extra][9][c_out].
+int extra_channel_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra,
+                       const float* w_extra, float* out, int B, int S, int c_out, int mode, cudaStream_t s);
+// final head: tmp[b][o][i][j] = W2[o] . relu(W1 v + b1) + b2[o] ; out = 0.5*(tmp + tmp^T), (B, O, S, S)
+bool final_head_ok(const ConvLayer& f0, const ConvLayer& f1);
 int final_head(const float* in /*[B][S][S][64]*/, const ConvLayer& f0, const ConvLayer& f1, float* tmp,
                float* out, int B, int S, cudaStream_t s);
 // Net.final_1d second conv + sigmoid: out[b][k][l] = sigmoid(b[k] + sum_c w[c][k] * in[b][l][c])

@@ -286,10 +286,10 @@ __device__ __forceinline__ float extra_src2(const float* sb, long long sH, long 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
-__global__ void extra_conv_planes_kernel(const float* __restrict__ src, long long sB, long long sH, long long sW,
-                                         const float* __restrict__ w /*[9][64]*/, __nv_bfloat16* __restrict__ hi,
-                                         __nv_bfloat16* __restrict__ lo, int S, int Wp, long long plane_rows, int mode,
-                                         long long total) {
+__global__ void extra_conv_planes_kernel(const float* __restrict__ src, long long sB, long long sC, long long sH, long long sW,
+                                         int n_extra, const float* __restrict__ w /*[n_extra][9][64]*/,
+                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int S, int Wp,
+                                         long long plane_rows, int mode, long long total) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % S);
     long long t = i / S;
@@ -297,37 +297,46 @@ __global__ void extra_conv_planes_kernel(const float* __restrict__ src, long lon
     t /= S;
     const int ch = (int)(t % 8);
     const long long b = t / 8;
-    const float* sb = src + b * sB;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < n_extra; ++e) {
+      const float* sb = src + b * sB + e * sC;
+      const float* we = w + e * 9 * 64;
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) {
-      const float v = extra_src2(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + tp * 64 + ch * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + tp * 64 + ch * 8 + 4));
-      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-      acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+      for (int tp = 0; tp < 9; ++tp) {
+        const float v = extra_src2(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(we + tp * 64 + ch * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(we + tp * 64 + ch * 8 + 4));
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+      }
     }
     const long long off = ((b * 8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
     split_store8(acc, hi + off, lo + off);
   }
 }
 
-// output head on planes: 1x1 64->5 (+BN) ReLU, 1x1 5->1  (orca_modules.py:423-428); one thread per pixel
+// output head on planes: 1x1 64->H (+BN) ReLU, 1x1 H->O  (orca_modules.py:423-428: H = 5, O = 1;
+// orca_leukemia.py:923-926: O = num_2d, H = max(num_2d, 5)); one thread per pixel, tmp is [nb][O][S][S]
+template <int H>
 __global__ void final_head_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                         const float* __restrict__ w0 /*[64][5]*/, const float* __restrict__ b0,
-                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                         float* __restrict__ tmp, int S, int Wp, long long plane_rows, long long total) {
-  __shared__ float sw[64 * 5 + 16];
-  for (int i = threadIdx.x; i < 320; i += blockDim.x) sw[i] = w0[i];
-  if (threadIdx.x < 5) { sw[320 + threadIdx.x] = b0[threadIdx.x]; sw[325 + threadIdx.x] = w1[threadIdx.x]; }
-  if (threadIdx.x == 0) sw[330] = b1[0];
+                                         const float* __restrict__ w0 /*[64][H]*/, const float* __restrict__ b0,
+                                         const float* __restrict__ w1 /*[H][O]*/, const float* __restrict__ b1,
+                                         float* __restrict__ tmp, int S, int Wp, long long plane_rows, long long total, int O) {
+  __shared__ float sw[64 * H], sb0[H], sw1[H * 8], sb1[8];
+  for (int i = threadIdx.x; i < 64 * H; i += blockDim.x) sw[i] = w0[i];
+  if (threadIdx.x < H) sb0[threadIdx.x] = b0[threadIdx.x];
+  if (threadIdx.x < H * O) sw1[threadIdx.x] = w1[threadIdx.x];
+  if (threadIdx.x < O) sb1[threadIdx.x] = b1[threadIdx.x];
   __syncthreads();
+  const long long img = (long long)S * S;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % S);
     const long long t = i / S;
     const int y = (int)(t % S);
     const long long b = t / S;
-    float h[5] = {0, 0, 0, 0, 0};
+    float h[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) h[k] = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
       float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -336,12 +345,16 @@ __global__ void final_head_planes_kernel(const __nv_bfloat16* __restrict__ hi, c
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int k = 0; k < 5; ++k) h[k] = fmaf(v[j], sw[(ch * 8 + j) * 5 + k], h[k]);
+        for (int k = 0; k < H; ++k) h[k] = fmaf(v[j], sw[(ch * 8 + j) * H + k], h[k]);
     }
-    float r = sw[330];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) r = fmaf(fmaxf(h[k] + sw[320 + k], 0.f), sw[325 + k], r);
-    tmp[i] = r;
+    for (int k = 0; k < H; ++k) h[k] = fmaxf(h[k] + sb0[k], 0.f);
+    for (int o = 0; o < O; ++o) {
+      float r = sb1[o];
+#pragma unroll
+      for (int k = 0; k < H; ++k) r = fmaf(h[k], sw1[k * O + o], r);
+      tmp[(b * O + o) * img + (long long)y * S + x] = r;
+    }
   }
 }
 
@@ -469,20 +482,29 @@ int tc_outer_sum(const float* xcl, TcMap* out, cudaStream_t s) {
   return ORCA_B200_OK;
 }
 
-int tc_extra_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra, TcMap* out, int mode, cudaStream_t s) {
-  if (out->C != 64) { set_error("tc_extra_conv: C != 64"); return ORCA_B200_EINVAL; }
+int tc_extra_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra, const float* w_extra,
+                  TcMap* out, int mode, cudaStream_t s) {
+  if (out->C != 64 || n_extra < 1) { set_error("tc_extra_conv: C != 64 or no extra channels"); return ORCA_B200_EINVAL; }
   const long long total = (long long)out->nb * 8 * out->S * out->S;
-  extra_conv_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, sB, sH, sW, w_extra, static_cast<__nv_bfloat16*>(out->hi),
+  extra_conv_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, sB, sC, sH, sW, n_extra, w_extra, static_cast<__nv_bfloat16*>(out->hi),
                                                            static_cast<__nv_bfloat16*>(out->lo), out->S, out->Wp, out->plane_rows, mode, total);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }
 
 int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp, cudaStream_t s) {
-  if (in.C != 64 || f0.c_in != 64 || f0.c_out != 5 || f1.c_in != 5 || f1.c_out != 1) { set_error("tc_final_head: bad layers"); return ORCA_B200_EINVAL; }
+  if (in.C != 64 || !final_head_ok(f0, f1)) { set_error("tc_final_head: bad layers (64->%d->%d)", f0.c_out, f1.c_out); return ORCA_B200_EINVAL; }
   const long long total = (long long)in.nb * in.S * in.S;
-  final_head_planes_kernel<<<grid_for(total), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in.hi), static_cast<const __nv_bfloat16*>(in.lo),
-                                                           f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total);
+  const __nv_bfloat16* hi = static_cast<const __nv_bfloat16*>(in.hi);
+  const __nv_bfloat16* lo = static_cast<const __nv_bfloat16*>(in.lo);
+  const unsigned g = grid_for(total);
+  const int O = f1.c_out;
+  switch (f0.c_out) {
+    case 5: final_head_planes_kernel<5><<<g, 256, 0, s>>>(hi, lo, f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total, O); break;
+    case 6: final_head_planes_kernel<6><<<g, 256, 0, s>>>(hi, lo, f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total, O); break;
+    case 7: final_head_planes_kernel<7><<<g, 256, 0, s>>>(hi, lo, f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total, O); break;
+    default: final_head_planes_kernel<8><<<g, 256, 0, s>>>(hi, lo, f0.w, f0.b, f1.w, f1.b, tmp, in.S, in.Wp, in.plane_rows, total, O); break;
+  }
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }

@@ -156,11 +156,12 @@ __device__ __forceinline__ float extra_src(const float* sb, long long sH, long l
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
-__global__ void extra_channel_conv_kernel(const float* __restrict__ src, long long sB, long long sH,
-                                          long long sW, const float* __restrict__ w /*[9][c_out]*/,
+__global__ void extra_channel_conv_kernel(const float* __restrict__ src, long long sB, long long sC, long long sH,
+                                          long long sW, int n_extra, const float* __restrict__ w /*[n_extra][9][c_out]*/,
                                           float* __restrict__ out, int S, int c_out, int mode,
                                           long long n_pix) {
-  // one warp-quarter (8 lanes... ) kept simple: thread = (pixel, 4 channels)
+  // thread = (pixel, 4 output channels); the n_extra source channels (1 in orca_modules, num_2d in
+  // orca_leukemia.py:931-951) are summed in channel order
   const int C4 = c_out >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -170,60 +171,67 @@ __global__ void extra_channel_conv_kernel(const float* __restrict__ src, long lo
     const long long by = pix / S;
     const int yy = (int)(by % S);
     const long long b = by / S;
-    const float* sb = src + b * sB;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < n_extra; ++e) {
+      const float* sb = src + b * sB + e * sC;
+      const float* we = w + (long long)e * 9 * c_out;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float v = extra_src(sb, sH, sW, S, mode, yy + t / 3 - 1, xx + t % 3 - 1);
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + t * c_out) + c);
-      acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y);
-      acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+      for (int t = 0; t < 9; ++t) {
+        const float v = extra_src(sb, sH, sW, S, mode, yy + t / 3 - 1, xx + t % 3 - 1);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(we + t * c_out) + c);
+        acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y);
+        acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+      }
     }
     reinterpret_cast<float4*>(out)[i] = acc;
   }
 }
 
-int extra_channel_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra,
-                       float* out, int B, int S, int c_out, int mode, cudaStream_t s) {
-  if (c_out % 4 || (mode != 0 && (S & 1))) { set_error("extra_channel_conv: bad geometry"); return ORCA_B200_EINVAL; }
+int extra_channel_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra,
+                       const float* w_extra, float* out, int B, int S, int c_out, int mode, cudaStream_t s) {
+  if (c_out % 4 || (mode != 0 && (S & 1)) || n_extra < 1) { set_error("extra_channel_conv: bad geometry"); return ORCA_B200_EINVAL; }
   const long long n_pix = (long long)B * S * S;
   if (n_pix == 0) return ORCA_B200_OK;
   unsigned grid = blocks_for(n_pix * (c_out / 4), 256);
   if (grid > 148u * 32u) grid = 148u * 32u;
-  extra_channel_conv_kernel<<<grid, 256, 0, s>>>(src, sB, sH, sW, w_extra, out, S, c_out, mode, n_pix);
+  extra_channel_conv_kernel<<<grid, 256, 0, s>>>(src, sB, sC, sH, sW, n_extra, w_extra, out, S, c_out, mode, n_pix);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }
 
-// ---- output head: 1x1 64->5 (+BN folded) + ReLU + 1x1 5->1, then symmetrise -----------------------
-// (orca_modules.py:423-428 and :487-488).  One warp per pixel row segment: each lane holds
-// 2 of the 64 channels, the five hidden units are reduced with warp shuffles.
-__global__ void final_head_kernel(const float* __restrict__ in, const float* __restrict__ w0 /*[64][5]*/,
-                                  const float* __restrict__ b0, const float* __restrict__ w1 /*[5]*/,
-                                  const float* __restrict__ b1, float* __restrict__ tmp, long long n_pix) {
+// ---- output head: 1x1 64->H (+BN folded) + ReLU + 1x1 H->O, then symmetrise ------------------------
+// (orca_modules.py:423-428 and :487-488: H = 5, O = 1; orca_leukemia.py:923-926: O = num_2d, H = max(num_2d, 5)).
+// One warp per pixel: each lane holds 2 of the 64 channels, the H hidden units are reduced with warp shuffles.
+// tmp is [B][O][S][S].
+template <int H>
+__global__ void final_head_kernel(const float* __restrict__ in, const float* __restrict__ w0 /*[64][H]*/,
+                                  const float* __restrict__ b0, const float* __restrict__ w1 /*[H][O]*/,
+                                  const float* __restrict__ b1, float* __restrict__ tmp, long long n_pix,
+                                  long long img /*S*S*/, int O) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  float wa[5], wb[5];
+  float wa[H], wb[H];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    wa[k] = __ldg(w0 + (2 * lane) * 5 + k);
-    wb[k] = __ldg(w0 + (2 * lane + 1) * 5 + k);
+  for (int k = 0; k < H; ++k) {
+    wa[k] = __ldg(w0 + (2 * lane) * H + k);
+    wb[k] = __ldg(w0 + (2 * lane + 1) * H + k);
   }
   for (long long p = warp; p < n_pix; p += nwarps) {
     const float2 v = __ldg(reinterpret_cast<const float2*>(in + p * 64) + lane);
-    float h[5];
+    float h[H];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) h[k] = fmaf(v.x, wa[k], v.y * wb[k]);
+    for (int k = 0; k < H; ++k) h[k] = fmaf(v.x, wa[k], v.y * wb[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int k = 0; k < 5; ++k) h[k] += __shfl_xor_sync(0xffffffffu, h[k], o);
-    if (lane == 0) {
-      float r = __ldg(b1);
+      for (int k = 0; k < H; ++k) h[k] += __shfl_xor_sync(0xffffffffu, h[k], o);
+    if (lane < O) {  // lane o evaluates output channel o
+      const long long b = p / img, q = p - b * img;
+      float r = __ldg(b1 + lane);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) r = fmaf(fmaxf(h[k] + __ldg(b0 + k), 0.f), __ldg(w1 + k), r);
-      tmp[p] = r;
+      for (int k = 0; k < H; ++k) r = fmaf(fmaxf(h[k] + __ldg(b0 + k), 0.f), __ldg(w1 + k * O + lane), r);
+      tmp[(b * O + lane) * img + q] = r;
     }
   }
 }
@@ -253,19 +261,27 @@ int symmetrise(const float* tmp, float* out, int B, int S, cudaStream_t s) {
   return ORCA_B200_OK;
 }
 
+bool final_head_ok(const ConvLayer& f0, const ConvLayer& f1) {
+  return f0.c_in == 64 && f0.c_out >= 5 && f0.c_out <= 8 && f1.c_in == f0.c_out && f1.c_out >= 1 && f1.c_out <= 8 &&
+         f0.kh == 1 && f0.kw == 1 && f1.kh == 1 && f1.kw == 1;
+}
+
 int final_head(const float* in, const ConvLayer& f0, const ConvLayer& f1, float* tmp, float* out, int B,
                int S, cudaStream_t s) {
-  if (f0.c_in != 64 || f0.c_out != 5 || f1.c_in != 5 || f1.c_out != 1) { set_error("final_head: bad layers"); return ORCA_B200_EINVAL; }
-  const long long n_pix = (long long)B * S * S;
+  if (!final_head_ok(f0, f1)) { set_error("final_head: bad layers (64->%d->%d)", f0.c_out, f1.c_out); return ORCA_B200_EINVAL; }
+  const long long n_pix = (long long)B * S * S, img = (long long)S * S;
   if (n_pix == 0) return ORCA_B200_OK;
   unsigned grid = blocks_for(n_pix, 8);
   if (grid > 148u * 16u) grid = 148u * 16u;
-  final_head_kernel<<<grid, 256, 0, s>>>(in, f0.w, f0.b, f1.w, f1.b, tmp, n_pix);
+  const int O = f1.c_out;
+  switch (f0.c_out) {
+    case 5: final_head_kernel<5><<<grid, 256, 0, s>>>(in, f0.w, f0.b, f1.w, f1.b, tmp, n_pix, img, O); break;
+    case 6: final_head_kernel<6><<<grid, 256, 0, s>>>(in, f0.w, f0.b, f1.w, f1.b, tmp, n_pix, img, O); break;
+    case 7: final_head_kernel<7><<<grid, 256, 0, s>>>(in, f0.w, f0.b, f1.w, f1.b, tmp, n_pix, img, O); break;
+    default: final_head_kernel<8><<<grid, 256, 0, s>>>(in, f0.w, f0.b, f1.w, f1.b, tmp, n_pix, img, O); break;
+  }
   ORCA_LAUNCH_OK();
-  dim3 g2((S + 31) / 32, (S + 31) / 32, B), b2(32, 8);
-  symmetrise_kernel<<<g2, b2, 0, s>>>(tmp, out, S);
-  ORCA_LAUNCH_OK();
-  return ORCA_B200_OK;
+  return symmetrise(tmp, out, B * O, S, s);
 }
 
 // ---- Net.final_1d tail: Conv1d(128 -> num_1d, k=1) + Sigmoid (orca_modules.py:1824-1830) ---------

@@ -54,23 +54,26 @@ static void spec_pairs(std::vector<Spec>& v, const int* dil, int n, int first_ci
     v.push_back({32, 64, 3, 3, dil[i]});
   }
 }
-static void spec_final(std::vector<Spec>& v) {
-  v.push_back({64, 5, 1, 1, 1});
-  v.push_back({5, 1, 1, 1, 1});
+// num_2d = number of predicted maps: 1 in orca_modules.py; orca_leukemia.py:512-993 parametrises the same trees
+// (final 64 -> max(num_2d,5) -> num_2d, combiner inputs 64+num_2d / 128+num_2d channels)
+static void spec_final(std::vector<Spec>& v, int num_2d) {
+  const int h = num_2d > 5 ? num_2d : 5;
+  v.push_back({64, h, 1, 1, 1});
+  v.push_back({h, num_2d, 1, 1, 1});
 }
-static void spec_decoder(std::vector<Spec>& v) {  // orca_modules.py:22-459
+static void spec_decoder(std::vector<Spec>& v, int num_2d) {  // orca_modules.py:22-459
   spec_pairs(v, kDecDil, 28, 64);                 // lconvtwos
   spec_pairs(v, kDecDil, 28, 64);                 // convtwos
-  spec_final(v);                                  // final
-  v.push_back({65, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // lcombiner
-  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // combiner
-  v.push_back({129, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});  // lcombinerD
-  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // combinerD
+  spec_final(v, num_2d);                          // final
+  v.push_back({64 + num_2d, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});   // lcombiner
+  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});            // combiner
+  v.push_back({128 + num_2d, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});  // lcombinerD
+  v.push_back({64, 64, 3, 3, 1}); v.push_back({64, 64, 3, 3, 1});            // combinerD
 }
-static void spec_decoder_1m(std::vector<Spec>& v) {  // orca_modules.py:499-780
+static void spec_decoder_1m(std::vector<Spec>& v, int num_2d) {  // orca_modules.py:499-780
   spec_pairs(v, kDec1mDil, 19, 128);
   spec_pairs(v, kDec1mDil, 19, 64);
-  spec_final(v);
+  spec_final(v, num_2d);
 }
 
 // index helpers into module->L
@@ -89,6 +92,7 @@ struct orca_b200_module {
   int kind = 0;
   uint32_t flags = 0;
   int num_1d = 0;
+  int num_2d = 1;  // output maps of Decoder / Decoder_1m / Net
   int device = 0;
   std::vector<ConvLayer> L;
   std::vector<void*> allocs;
@@ -498,9 +502,15 @@ static int bottleneck(const ConvLayer* lm, const ConvLayer* mm, const float*& cu
   return ORCA_B200_OK;
 }
 
+struct Plane4 {  // a (B, C, H, W) fp32 input given by pointer + element strides
+  const float* p = nullptr;
+  int64_t sB = 0, sC = 0, sH = 0, sW = 0;
+};
+
 static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl /*[B][S][128]*/,
-                        int B, int S, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
-                        int64_t ysB, int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+                        int B, int S, const Plane4& de, const Plane4& yc, float* out, Arena& ar, cudaStream_t s) {
+  const float* distenc = de.p;
+  const float* y = yc.p;
   const size_t mk = ar.mark();
   const size_t pix = (size_t)B * S * S;
   float* mat = ar.f32(pix * 128);
@@ -510,7 +520,7 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
   rot.t[2] = ar.f32(pix * 64);
   float* Hbuf = ar.f32(pix * 64);
   float* E = is_1m ? nullptr : ar.f32(pix * 64);
-  float* tmp = ar.f32(pix);
+  float* tmp = ar.f32(pix * m->num_2d);
   ARENA_OK(ar);
   if (!ar.dry) {
     ORCA_TRY(outer_sum(xcl, mat, B, 128, S, s));
@@ -525,7 +535,7 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
       ConvCall c;
       c.B = B; c.H = S; c.W = S; c.res_ld = 64;
       // mat = lcombinerD(cat(mat, distenc)) ; mat = combinerD(mat) + mat      (:463-465)
-      ORCA_TRY(extra_channel_conv(distenc, dsB, dsH, dsW, L[DEC_LCOMBD].w_extra, E, B, S, 64, 0, s));
+      ORCA_TRY(extra_channel_conv(distenc, de.sB, de.sC, de.sH, de.sW, L[DEC_LCOMBD].n_extra, L[DEC_LCOMBD].w_extra, E, B, S, 64, 0, s));
       float* a0 = rot.next();
       c.in = mat; c.in_ld = 128; c.out = a0; c.out_ld = 64; c.relu = 0; c.res = E;
       ORCA_TRY(conv(L[DEC_LCOMBD], c, s));
@@ -542,7 +552,7 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
       if (y) {
         // cur = lcombiner(cat(mat, upsample(y))) ; cur = combiner(cur) + cur   (:467-474)
         const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
-        ORCA_TRY(extra_channel_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, E, B, S, 64, mode, s));
+        ORCA_TRY(extra_channel_conv(y, yc.sB, yc.sC, yc.sH, yc.sW, L[DEC_LCOMB].n_extra, L[DEC_LCOMB].w_extra, E, B, S, 64, mode, s));
         float* b0 = rot.next();
         c.in = cur; c.out = b0; c.relu = 0; c.res = E;
         ORCA_TRY(conv(L[DEC_LCOMB], c, s));
@@ -630,8 +640,9 @@ static int bottleneck_tc(const ConvLayer* lm, const ConvLayer* mm, TcMap& cur, b
 }
 
 static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl, int B, int S,
-                           const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y, int64_t ysB,
-                           int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+                           const Plane4& de, const Plane4& yc, float* out, Arena& ar, cudaStream_t s) {
+  const float* distenc = de.p;
+  const float* y = yc.p;
   const size_t mk = ar.mark();
   const size_t b64 = 2 * tc2d_plane_bytes(B, 64, S);
   void* matb = ar.raw(2 * b64);  // 128 channels
@@ -642,7 +653,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
   void* ebuf = is_1m ? nullptr : ar.raw(b64);
   void* ebuf2 = is_1m ? nullptr : ar.raw(b64);  // coarse-map term (kept apart from the distance term: both are
                                                 // computed before the conv program runs)
-  float* tmp = ar.f32((size_t)B * S * S);
+  float* tmp = ar.f32((size_t)B * S * S * m->num_2d);
   const size_t prog_bytes = Tc2dProgram::scratch_bytes(128);
   void* prog_scratch = ar.raw(prog_bytes);
   ARENA_OK(ar);
@@ -682,7 +693,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       ORCA_TRY(tc_final_head_tmp(cur, L[D1M_FINAL], L[D1M_FINAL + 1], tmp, s));
     } else {
       TcMap E = map_make(ebuf, B, 64, S);
-      ORCA_TRY(tc_extra_conv(distenc, dsB, dsH, dsW, L[DEC_LCOMBD].w_extra, &E, 0, s));
+      ORCA_TRY(tc_extra_conv(distenc, de.sB, de.sC, de.sH, de.sW, L[DEC_LCOMBD].n_extra, L[DEC_LCOMBD].w_extra, &E, 0, s));
       TcMap a0 = rot.next();
       ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMBD], mat, &E, &a0, 0, s));
       TcMap a1 = rot.next();
@@ -695,7 +706,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       if (y) {
         const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
         TcMap E2 = map_make(ebuf2, B, 64, S);
-        ORCA_TRY(tc_extra_conv(y, ysB, ysH, ysW, L[DEC_LCOMB].w_extra, &E2, mode, s));
+        ORCA_TRY(tc_extra_conv(y, yc.sB, yc.sC, yc.sH, yc.sW, L[DEC_LCOMB].n_extra, L[DEC_LCOMB].w_extra, &E2, mode, s));
         TcMap b0 = rot.next();
         ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB], cur, &E2, &b0, 0, s));
         TcMap b1 = rot.next();
@@ -713,7 +724,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
       ORCA_TRY(flush());
       ORCA_TRY(tc_final_head_tmp(cur, L[DEC_FINAL], L[DEC_FINAL + 1], tmp, s));
     }
-    ORCA_TRY(symmetrise(tmp, out, B, S, s));
+    ORCA_TRY(symmetrise(tmp, out, B * m->num_2d, S, s));
   }
   ar.release(mk);
   return ORCA_B200_OK;
@@ -728,22 +739,18 @@ static bool use_tc_decoder(const ConvLayer* L, bool is_1m) {
 }
 
 static int decoder_body_any(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl, int B, int S,
-                            const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y, int64_t ysB,
-                            int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
-  if (use_tc_decoder(L, is_1m))
-    return decoder_body_tc(m, L, is_1m, xcl, B, S, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar, s);
-  return decoder_body(m, L, is_1m, xcl, B, S, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar, s);
+                            const Plane4& de, const Plane4& yc, float* out, Arena& ar, cudaStream_t s) {
+  if (use_tc_decoder(L, is_1m)) return decoder_body_tc(m, L, is_1m, xcl, B, S, de, yc, out, ar, s);
+  return decoder_body(m, L, is_1m, xcl, B, S, de, yc, out, ar, s);
 }
 
 static int decoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t S, int64_t xsB, int64_t xsC,
-                       int64_t xsL, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
-                       int64_t ysB, int64_t ysH, int64_t ysW, float* out, Arena& ar, cudaStream_t s) {
+                       int64_t xsL, const Plane4& de, const Plane4& yc, float* out, Arena& ar, cudaStream_t s) {
   const size_t mk = ar.mark();
   float* xcl = ar.f32((size_t)B * S * 128);
   ARENA_OK(ar);
   if (!ar.dry) ORCA_TRY(to_channel_last(x, xsB, xsC, xsL, xcl, (int)B, 128, S, s));
-  ORCA_TRY(decoder_body_any(m, m->L.data(), m->kind == ORCA_B200_DECODER_1M, xcl, (int)B, (int)S, distenc, dsB, dsH,
-                            dsW, y, ysB, ysH, ysW, out, ar, s));
+  ORCA_TRY(decoder_body_any(m, m->L.data(), m->kind == ORCA_B200_DECODER_1M, xcl, (int)B, (int)S, de, yc, out, ar, s));
   ar.release(mk);
   return ORCA_B200_OK;
 }
@@ -757,7 +764,7 @@ static int net_run(const orca_b200_module* m, const float* x, int64_t B, int64_t
   ARENA_OK(ar);
   for (int64_t b = 0; b < B; ++b)
     ORCA_TRY(encoder_window_any(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
-  ORCA_TRY(decoder_body_any(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, nullptr, 0, 0, 0, nullptr, 0, 0, 0, out, ar, s));
+  ORCA_TRY(decoder_body_any(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, Plane4(), Plane4(), out, ar, s));
   if (m->num_1d > 0 && out_1d) {  // final_1d (orca_modules.py:1824-1830, :1852-1853)
     float* h = ar.f32((size_t)B * S * 128);
     ARENA_OK(ar);
@@ -785,12 +792,12 @@ static int upload(const std::vector<float>& h, float** d, std::vector<void*>& al
   return ORCA_B200_OK;
 }
 
-static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<void*>& allocs,
+static int pack_layer(const orca_b200_conv_params& p, int n_extra, ConvLayer& L, std::vector<void*>& allocs,
                       std::vector<float>* keep_w = nullptr, std::vector<float>* keep_b = nullptr) {
   const int taps = p.kh * p.kw;
-  const bool odd = (p.c_in == 129 || p.c_in == 65);
-  const int cin_main = odd ? p.c_in - 1 : p.c_in;
-  L.c_in = cin_main; L.c_out = p.c_out; L.kh = p.kh; L.kw = p.kw; L.dil = p.dilation;
+  const bool odd = n_extra > 0;  // trailing input channels evaluated outside the aligned implicit GEMM
+  const int cin_main = p.c_in - n_extra;
+  L.c_in = cin_main; L.c_out = p.c_out; L.kh = p.kh; L.kw = p.kw; L.dil = p.dilation; L.n_extra = n_extra;
   std::vector<double> scale(p.c_out, 1.0), shift(p.c_out, 0.0);
   const bool bn = p.bn_weight && p.bn_bias && p.bn_mean && p.bn_var;
   for (int co = 0; co < p.c_out; ++co) {
@@ -804,14 +811,14 @@ static int pack_layer(const orca_b200_conv_params& p, ConvLayer& L, std::vector<
     }
   }
   std::vector<float> w((size_t)taps * cin_main * p.c_out), bias(p.c_out), wx;
-  if (odd) wx.resize((size_t)taps * p.c_out);
+  if (odd) wx.resize((size_t)n_extra * taps * p.c_out);
   for (int co = 0; co < p.c_out; ++co) {
     bias[co] = (float)shift[co];
     for (int ci = 0; ci < p.c_in; ++ci)
       for (int t = 0; t < taps; ++t) {
         const float v = (float)((double)p.weight[((size_t)co * p.c_in + ci) * taps + t] * scale[co]);
         if (ci < cin_main) w[((size_t)t * cin_main + ci) * p.c_out + co] = v;
-        else wx[(size_t)t * p.c_out + co] = v;
+        else wx[((size_t)(ci - cin_main) * taps + t) * p.c_out + co] = v;
       }
   }
   ORCA_TRY(upload(w, &L.w, allocs));
@@ -863,16 +870,24 @@ int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_
   if (!convs || !out) { set_error("module_create: NULL argument"); return ORCA_B200_EINVAL; }
   *out = nullptr;
   std::vector<Spec> spec;
+  // num_2d (output maps) is read off the module's own final 1x1 conv and then checked like everything else
+  int num_2d = 1;
+  {
+    const int fin = kind == ORCA_B200_DECODER ? DEC_FINAL + 1 : kind == ORCA_B200_DECODER_1M ? D1M_FINAL + 1
+                    : kind == ORCA_B200_NET ? ENC_N + D1M_FINAL + 1 : -1;
+    if (fin >= 0 && fin < n_convs) num_2d = convs[fin].c_out;
+    if (num_2d < 1 || num_2d > 8) { set_error("module_create: num_2d=%d outside [1, 8]", num_2d); return ORCA_B200_EINVAL; }
+  }
   switch (kind) {
     case ORCA_B200_ENCODER: spec_encoder(spec); break;
     case ORCA_B200_ENCODER2: spec_unet(spec, 5, true); break;
     case ORCA_B200_ENCODER2B: spec_unet(spec, 5, false); break;
     case ORCA_B200_ENCODER3: spec_unet(spec, 3, true); break;
-    case ORCA_B200_DECODER: spec_decoder(spec); break;
-    case ORCA_B200_DECODER_1M: spec_decoder_1m(spec); break;
+    case ORCA_B200_DECODER: spec_decoder(spec, num_2d); break;
+    case ORCA_B200_DECODER_1M: spec_decoder_1m(spec, num_2d); break;
     case ORCA_B200_NET:
       spec_encoder(spec);
-      spec_decoder_1m(spec);
+      spec_decoder_1m(spec, num_2d);
       if (num_1d > 0) { spec.push_back({128, 128, 1, 1, 1}); spec.push_back({128, num_1d, 1, 1, 1}); }
       break;
     default: set_error("module_create: unknown module kind %d", kind); return ORCA_B200_EINVAL;
@@ -896,13 +911,14 @@ int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_
   }
   orca_b200_module* m = new (std::nothrow) orca_b200_module();
   if (!m) { set_error("module_create: out of host memory"); return ORCA_B200_EINVAL; }
-  m->kind = kind; m->flags = flags; m->num_1d = num_1d;
+  m->kind = kind; m->flags = flags; m->num_1d = num_1d; m->num_2d = num_2d;
   if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); delete m; set_error("module_create: no CUDA device"); return ORCA_B200_ECUDA; }
   m->L.resize(n_convs);
   std::vector<float> head_w[2], head_b[2];
   for (int i = 0; i < n_convs; ++i) {
     const bool enc_head = (kind == ORCA_B200_ENCODER || kind == ORCA_B200_NET) && i < 2;  // lconv1[0], lconv1[1]
-    int st = pack_layer(convs[i], m->L[i], m->allocs, enc_head ? &head_w[i] : nullptr, enc_head ? &head_b[i] : nullptr);
+    const int n_extra = (kind == ORCA_B200_DECODER && (i == DEC_LCOMB || i == DEC_LCOMBD)) ? num_2d : 0;
+    int st = pack_layer(convs[i], n_extra, m->L[i], m->allocs, enc_head ? &head_w[i] : nullptr, enc_head ? &head_b[i] : nullptr);
     if (st == ORCA_B200_OK && enc_head && i == 1)
       st = tc_pack_lconv1(m->L[0], head_w[0].data(), head_b[0].data(), head_w[1].data(), head_b[1].data(), m->allocs);
     if (st != ORCA_B200_OK) { orca_b200_module_destroy(m); return st; }
@@ -918,6 +934,7 @@ void orca_b200_module_destroy(orca_b200_module* m) {
 }
 
 int orca_b200_module_kind(const orca_b200_module* m) { return m ? m->kind : 0; }
+int orca_b200_module_num_2d(const orca_b200_module* m) { return m ? m->num_2d : 0; }
 
 // ---- Encoder -----------------------------------------------------------------------------------
 static int encoder_args_ok(const orca_b200_module* m, int64_t B, int64_t L, int64_t b0, int64_t b1) {
@@ -1006,14 +1023,14 @@ static int decoder_args_ok(const orca_b200_module* m, int64_t B, int64_t S) {
 size_t orca_b200_decoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t S) {
   if (decoder_args_ok(m, B, S) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
-  decoder_run(m, nullptr, B, S, 0, 0, 0, nullptr, 0, 0, 0, nullptr, 0, 0, 0, nullptr, ar, nullptr);
+  decoder_run(m, nullptr, B, S, 0, 0, 0, Plane4(), Plane4(), nullptr, ar, nullptr);
   return ar.peak + 256;
 }
 
 int orca_b200_decoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t S, int64_t xsB, int64_t xsC,
-                              int64_t xsL, const float* distenc, int64_t dsB, int64_t dsH, int64_t dsW, const float* y,
-                              int64_t ysB, int64_t ysH, int64_t ysW, float* out, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              int64_t xsL, const float* distenc, int64_t dsB, int64_t dsC, int64_t dsH, int64_t dsW,
+                              const float* y, int64_t ysB, int64_t ysC, int64_t ysH, int64_t ysW, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   ORCA_TRY(decoder_args_ok(m, B, S));
   ORCA_TRY(check_ptr_device(x, "decoder: x"));
   ORCA_TRY(check_ptr_device(out, "decoder: out"));
@@ -1028,8 +1045,10 @@ int orca_b200_decoder_forward(const orca_b200_module* m, const float* x, int64_t
     set_error("decoder: Decoder_1m takes neither distenc nor y"); return ORCA_B200_EINVAL;
   }
   Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
-  return decoder_run(m, x, B, S, xsB, xsC, xsL, distenc, dsB, dsH, dsW, y, ysB, ysH, ysW, out, ar,
-                     static_cast<cudaStream_t>(stream));
+  Plane4 de, yc;
+  de.p = distenc; de.sB = dsB; de.sC = dsC; de.sH = dsH; de.sW = dsW;
+  yc.p = y; yc.sB = ysB; yc.sC = ysC; yc.sH = ysH; yc.sW = ysW;
+  return decoder_run(m, x, B, S, xsB, xsC, xsL, de, yc, out, ar, static_cast<cudaStream_t>(stream));
 }
 
 // ---- Net ---------------------------------------------------------------------------------------

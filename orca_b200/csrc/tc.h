@@ -53,9 +53,9 @@ bool tc_layer2d_eligible(const ConvLayer& L);
 int tc_pack_layer2d(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
 int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s);
 int tc_outer_sum(const float* xcl /*[nb][S][C]*/, TcMap* out, cudaStream_t s);
-int tc_extra_conv(const float* src, int64_t sB, int64_t sH, int64_t sW, const float* w_extra, TcMap* out, int mode,
-                  cudaStream_t s);
-int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp /*[nb][S][S]*/, cudaStream_t s);
+int tc_extra_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra, const float* w_extra,
+                  TcMap* out, int mode, cudaStream_t s);
+int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp /*[nb][O][S][S]*/, cudaStream_t s);
 
 // All the 3x3 convs of one decoder call as ONE persistent kernel with grid barriers between layers
 // (conv2d_prog.cu).  add() records a layer, run() uploads the layer table into `scratch` and launches.

@@ -2,7 +2,8 @@
 Model shells: the attribute protocol `orca_predict.genomepredict*` drives
 (`.net0 .net [.net1] .denets{level} [.denet_1_pt] .normmats .epss [.background_cis/.background_trans]`),
 mirroring /root/reference/orca_models.py (H1esc :17-175, Hff :178-333, HCTnoc :335-446,
-H1esc_1M :449-494, Hff_1M :497-542, H1esc_256M :545-649, Hff_256M :652-760).
+H1esc_1M :449-494, Hff_1M :497-542, H1esc_256M :545-649, Hff_256M :652-760) and the two multi-dataset
+shells of /root/reference/orca_leukemia.py (OrcaLeukemiaA :1604-1733, OrcaLeukemiaB :1736-1876).
 
 The reference shells load trained weights from `ORCA_PATH/models/*.statedict` and background
 curves from `ORCA_PATH/resources/*.npy` (a Zenodo download, not in the repository).  Here:
@@ -105,6 +106,18 @@ def build_shell(classes, kind="h1esc", seed=0, orca_path=None):
                     _init(classes.Decoder(upsample_mode="bilinear"), base + _SEED_DEC + i, orca_path,
                           "orca_%s_256m.d%d.statedict" % (cell, level)))
         sh.background_cis, sh.background_trans = _background_256mb(orca_path, cell)
+    elif kind in ("leukemia_a", "leukemia_b"):
+        # orca_leukemia.py:1604-1876 (OrcaLeukemiaA: 2 datasets, OrcaLeukemiaB: 6); `classes` must expose the
+        # orca_leukemia signatures (orca_b200.leukemia, or the reference's orca_leukemia module)
+        n_files = 2 if kind == "leukemia_a" else 6
+        stem = "orca_leukemia" + kind[-1].upper()
+        sh.net0 = _init(classes.Encoder(), base + _SEED_NET0, orca_path, stem + ".net0.statedict", True)
+        sh.net = _init(classes.Encoder2(), base + _SEED_NET, orca_path, stem + ".net.statedict")
+        for i, level in enumerate(LEVELS_32M):
+            setattr(sh, "denet_%d" % level,
+                    _init(classes.Decoder(n_files), base + _SEED_DEC + i, orca_path, "%s.d%d.statedict" % (stem, level)))
+        sh.denet_1_pt = _init(classes.Decoder_1m(n_files), base + _SEED_D1PT, orca_path, stem + ".net0.statedict", True)
+        sh.normmats, sh.epss = _background_leukemia(orca_path, kind, n_files)
     else:
         raise ValueError("unknown shell kind %r" % kind)
     sh.eval()
@@ -129,6 +142,30 @@ def _background_32mb(orca_path, cell, res1000=False):
     return synthetic.normmats_32mb(elog)
 
 
+_LEUKEMIA_RES = {  # orca_leukemia.py:1631-1632, :1763-1768
+    "leukemia_a": ["GSE134761_TALL_all.hg38.no_filter.1000.mcool.expected.res4000.npy",
+                   "THP1.hg38.no_filter.1000.mcool.expected.res4000.npy"],
+    "leukemia_b": ["4DNFIXP4QG5B.mcool.rebinned.mcool.expected.res4000.npy",
+                   "NALM6.hg38.no_filter.1000.mcool.expected.res4000.npy",
+                   "GSE146901_T_ALL_NonETP.hg38.no_filter.1000.mcool.expected.res4000.npy",
+                   "GSE146901_T_ALL_ETP.hg38.no_filter.1000.mcool.expected.res4000.npy",
+                   "GSE63525_K562.hg38.no_filter.1000.mcool.expected.res4000.npy",
+                   "GSE63525_KBM7.hg38.no_filter.1000.mcool.expected.res4000.npy"],
+}
+
+
+def _background_leukemia(orca_path, kind, n_files):
+    """(n_files, 250, 250) block-mean backgrounds per level (orca_leukemia.py:1636-1643, :1706-1720)."""
+    if orca_path is None:
+        # synthetic: one power-law curve per dataset with slightly different exponents
+        elogs = [-(0.8 + 0.05 * i) * np.log(np.arange(8000, dtype=np.float64) + 1.0) - 3.0 for i in range(n_files)]
+    else:
+        elogs = [np.load(os.path.join(orca_path, "resources", f))[:8000] for f in _LEUKEMIA_RES[kind]]
+    per = [synthetic.normmats_32mb(e) for e in elogs]
+    mats = {lvl: np.stack([m[lvl] for m, _ in per], axis=0) for lvl in LEVELS_32M}
+    return mats, {lvl: np.min(mats[lvl]) for lvl in LEVELS_32M}
+
+
 def _background_256mb(orca_path, cell):
     # orca_models.py:626-633: exp(mono curve) padded with 2000 NaNs; exp(trans scalar)
     if orca_path is None:
@@ -141,7 +178,10 @@ def _background_256mb(orca_path, cell):
 
 
 def _native(kind, seed, orca_path, device):
-    from . import modules
+    if kind.startswith("leukemia"):
+        from . import leukemia as modules
+    else:
+        from . import modules
     sh = build_shell(modules, kind, seed, orca_path)
     return sh.to(device) if device is not None else sh
 
@@ -172,3 +212,11 @@ def H1esc_256M(seed=0, orca_path=None, device="cuda"):
 
 def Hff_256M(seed=1, orca_path=None, device="cuda"):
     return _native("hff_256m", seed, orca_path, device)
+
+
+def OrcaLeukemiaA(seed=4, orca_path=None, device="cuda"):
+    return _native("leukemia_a", seed, orca_path, device)
+
+
+def OrcaLeukemiaB(seed=5, orca_path=None, device="cuda"):
+    return _native("leukemia_b", seed, orca_path, device)

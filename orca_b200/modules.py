@@ -62,9 +62,17 @@ def _seq2d_relu(c_in, c_mid, c_out, d):
         nn.ReLU(inplace=True))
 
 
-def _final2d():
-    return nn.Sequential(nn.Conv2d(64, 5, kernel_size=(1, 1), padding=0), nn.BatchNorm2d(5),
-                         nn.ReLU(inplace=True), nn.Conv2d(5, 1, kernel_size=(1, 1), padding=0))
+def _final2d(num_2d=1):
+    """orca_modules.py:423-428 (num_2d = 1); orca_leukemia.py:923-926: hidden width max(num_2d, 5)."""
+    h = num_2d if num_2d > 5 else 5
+    return nn.Sequential(nn.Conv2d(64, h, kernel_size=(1, 1), padding=0), nn.BatchNorm2d(h),
+                         nn.ReLU(inplace=True), nn.Conv2d(h, num_2d, kernel_size=(1, 1), padding=0))
+
+
+def _check_num_2d(num_2d):
+    if not isinstance(num_2d, int) or not 1 <= num_2d <= 8:
+        raise ValueError("num_2d must be an int in [1, 8], got %r" % (num_2d,))
+    return num_2d
 
 
 def _add_encoder_stages(mod):
@@ -74,12 +82,12 @@ def _add_encoder_stages(mod):
         setattr(mod, "conv%d" % k, _seq1d_relu(c_out))
 
 
-def _add_decoder_1m_body(mod):
+def _add_decoder_1m_body(mod, num_2d=1):
     dil = DECODER_1M_DILATIONS
     mod.lconvtwos = nn.ModuleList(
         [_seq2d_linear(128 if i == 0 else 64, 32, 64, d, dropout=(i == 0)) for i, d in enumerate(dil)])
     mod.convtwos = nn.ModuleList([_seq2d_relu(64, 32, 64, d) for d in dil])
-    mod.final = _final2d()
+    mod.final = _final2d(num_2d)
 
 
 # ----------------------------------------------------------------------------------------
@@ -323,24 +331,26 @@ class Encoder2b(_UNet1d):
 
 
 class Decoder(_NativeModule):
-    """2D dilated-conv decoder head; mirrors orca_modules.Decoder (:16-488).
+    """2D dilated-conv decoder head; mirrors orca_modules.Decoder (:16-488) and, with num_2d > 1, the
+    multi-map orca_leukemia.Decoder (orca_leukemia.py:512-993; see orca_b200.leukemia for its signature).
 
-    forward(x f32[B,128,S], distenc f32[B,1,S,S], y f32[B,1,S/2,S/2] | None) -> f32[B,1,S,S]
+    forward(x f32[B,128,S], distenc f32[B,C,S,S], y f32[B,C,S/2,S/2] | None) -> f32[B,C,S,S]   (C = num_2d)
     """
     _kind = _lib.DECODER
 
-    def __init__(self, upsample_mode="nearest"):
+    def __init__(self, upsample_mode="nearest", num_2d=1):
         super().__init__()
         if upsample_mode not in ("nearest", "bilinear"):
             raise ValueError("upsample_mode must be 'nearest' or 'bilinear'")
+        self.num_2d = _check_num_2d(num_2d)
         dil = DECODER_DILATIONS
         self.lconvtwos = nn.ModuleList([_seq2d_linear(64, 32, 64, d, dropout=(i == 0)) for i, d in enumerate(dil)])
         self.convtwos = nn.ModuleList([_seq2d_relu(64, 32, 64, d) for d in dil])
-        self.final = _final2d()
+        self.final = _final2d(num_2d)
         self.upsample = nn.Upsample(scale_factor=(2, 2), mode=upsample_mode)
-        self.lcombiner = _seq2d_linear(65, 64, 64, 1, dropout=True)
+        self.lcombiner = _seq2d_linear(64 + num_2d, 64, 64, 1, dropout=True)
         self.combiner = _seq2d_relu(64, 64, 64, 1)
-        self.lcombinerD = _seq2d_linear(129, 64, 64, 1)
+        self.lcombinerD = _seq2d_linear(128 + num_2d, 64, 64, 1)
         self.combinerD = _seq2d_relu(64, 64, 64, 1)
         self.eval()
 
@@ -357,33 +367,36 @@ class Decoder(_NativeModule):
         if x.dim() != 3 or x.size(1) != 128:
             raise RuntimeError("Decoder.forward: x must be (B, 128, S), got %s" % (tuple(x.shape),))
         B, _, S = x.shape
-        if tuple(distenc.shape) != (B, 1, S, S):
-            raise RuntimeError("Decoder.forward: distenc must be (%d, 1, %d, %d), got %s" % (B, S, S, tuple(distenc.shape)))
+        C = self.num_2d
+        if tuple(distenc.shape) != (B, C, S, S):
+            raise RuntimeError("Decoder.forward: distenc must be (%d, %d, %d, %d), got %s" % (B, C, S, S, tuple(distenc.shape)))
         if y is not None:
             _require_cuda("Decoder.forward(y)", y)
-            if S % 2 or tuple(y.shape) != (B, 1, S // 2, S // 2):
-                raise RuntimeError("Decoder.forward: y must be (%d, 1, %d, %d), got %s" % (B, S // 2, S // 2, tuple(y.shape)))
+            if S % 2 or tuple(y.shape) != (B, C, S // 2, S // 2):
+                raise RuntimeError("Decoder.forward: y must be (%d, %d, %d, %d), got %s" % (B, C, S // 2, S // 2, tuple(y.shape)))
         dev = x.device
         h = self.native_handle(dev)
         lib = _lib.lib()
         with torch.cuda.device(dev):
-            out = torch.empty((B, 1, S, S), dtype=torch.float32, device=dev)
+            out = torch.empty((B, C, S, S), dtype=torch.float32, device=dev)
             ws = _workspace(lib.orca_b200_decoder_workspace_bytes(h, B, S), dev)
-            yp, ys = (None, (0, 0, 0)) if y is None else (_ptr(y), (y.stride(0), y.stride(2), y.stride(3)))
+            yp, ys = (None, (0, 0, 0, 0)) if y is None else (_ptr(y), y.stride())
             _lib.check(lib.orca_b200_decoder_forward(
                 h, _ptr(x), B, S, x.stride(0), x.stride(1), x.stride(2),
-                _ptr(distenc), distenc.stride(0), distenc.stride(2), distenc.stride(3),
-                yp, ys[0], ys[1], ys[2], _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
+                _ptr(distenc), distenc.stride(0), distenc.stride(1), distenc.stride(2), distenc.stride(3),
+                yp, ys[0], ys[1], ys[2], ys[3], _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
         return out
 
 
 class Decoder_1m(_NativeModule):
-    """1 Mb decoder; mirrors orca_modules.Decoder_1m (:491-800).  forward(x f32[B,128,S]) -> f32[B,1,S,S]"""
+    """1 Mb decoder; mirrors orca_modules.Decoder_1m (:491-800) and, with num_2d > 1, orca_leukemia.Decoder_1m
+    (orca_leukemia.py:996-1315).  forward(x f32[B,128,S]) -> f32[B,num_2d,S,S]"""
     _kind = _lib.DECODER_1M
 
-    def __init__(self):
+    def __init__(self, num_2d=1):
         super().__init__()
-        _add_decoder_1m_body(self)
+        self.num_2d = _check_num_2d(num_2d)
+        _add_decoder_1m_body(self, num_2d)
         self.eval()
 
     def _sequentials(self):
@@ -398,22 +411,24 @@ class Decoder_1m(_NativeModule):
         h = self.native_handle(dev)
         lib = _lib.lib()
         with torch.cuda.device(dev):
-            out = torch.empty((B, 1, S, S), dtype=torch.float32, device=dev)
+            out = torch.empty((B, self.num_2d, S, S), dtype=torch.float32, device=dev)
             ws = _workspace(lib.orca_b200_decoder_workspace_bytes(h, B, S), dev)
             _lib.check(lib.orca_b200_decoder_forward(
-                h, _ptr(x), B, S, x.stride(0), x.stride(1), x.stride(2), None, 0, 0, 0, None, 0, 0, 0,
+                h, _ptr(x), B, S, x.stride(0), x.stride(1), x.stride(2), None, 0, 0, 0, 0, None, 0, 0, 0, 0,
                 _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
         return out
 
 
 class Net(_NativeModule):
-    """Orca-1Mb (Encoder body + Decoder_1m body [+ final_1d]); mirrors orca_modules.Net (:1409-1900)."""
+    """Orca-1Mb (Encoder body + Decoder_1m body [+ final_1d]); mirrors orca_modules.Net (:1409-1900) and, with
+    num_2d > 1, orca_leukemia.Net (orca_leukemia.py:16-509)."""
     _kind = _lib.NET
 
-    def __init__(self, num_1d=None):
+    def __init__(self, num_1d=None, num_2d=1):
         super().__init__()
+        self.num_2d = _check_num_2d(num_2d)
         _add_encoder_stages(self)
-        _add_decoder_1m_body(self)
+        _add_decoder_1m_body(self, num_2d)
         if num_1d is not None:
             self.final_1d = nn.Sequential(
                 nn.Conv1d(128, 128, kernel_size=1, padding=0), nn.BatchNorm1d(128), nn.ReLU(inplace=True),
@@ -444,7 +459,7 @@ class Net(_NativeModule):
         h = self.native_handle(dev)
         lib = _lib.lib()
         with torch.cuda.device(dev):
-            out = torch.empty((B, 1, S, S), dtype=torch.float32, device=dev)
+            out = torch.empty((B, self.num_2d, S, S), dtype=torch.float32, device=dev)
             out1d = torch.empty((B, self.num_1d, S), dtype=torch.float32, device=dev) if self.num_1d else None
             ws = _workspace(lib.orca_b200_net_workspace_bytes(h, B, L), dev)
             _lib.check(lib.orca_b200_net_forward(h, _ptr(x), B, L, x.stride(0), x.stride(1), x.stride(2),

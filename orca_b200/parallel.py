@@ -53,7 +53,10 @@ class ShardedForward:
         self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         self.h2d_bytes = 0
-        self.d2h_bytes = 6 * 250 * 250 * 4 if rank == 0 else 0
+        # maps per level: 1, or num_2d for the multi-dataset shells of orca_leukemia.py
+        denets = getattr(shell, "denets", None) or {}
+        self.n_ch = int(getattr(next(iter(denets.values()), None), "num_2d", 1))
+        self.d2h_bytes = 6 * self.n_ch * 250 * 250 * 4 if rank == 0 else 0
 
     def set_background(self, normmat, chrlen):
         """256 Mb shells: the caller's (8000, 8000) background matrix at 32 kb bins (as passed to
@@ -134,7 +137,8 @@ class ShardedForward:
         return self._gather(self._encode_local(reverse), reverse)
 
     def forward(self, mpos, wpos):
-        """Returns the 6 strand-averaged maps (6, 250, 250) on rank 0 (None elsewhere)."""
+        """Returns the strand-averaged maps on rank 0 (None elsewhere): (6, 250, 250) for the 32 Mb shells,
+        (4, 250, 250) for the 256 Mb shells, (6, num_2d, 250, 250) for multi-dataset shells."""
         shell, world, rank = self.shell, self.world, self.rank
         with torch.no_grad():
             if self.concurrent_strands and self.device.type == "cuda":
@@ -173,7 +177,7 @@ class ShardedForward:
                     p = predict.cascade_256mb(shell, finest(rev), 1, self.background, self.chrlen, mpos, wpos, rev)[0]
                 else:
                     p, _ = predict.cascade_32mb(shell, finest(rev), 1, mpos, wpos, rev, inline_1m=False)
-                return torch.cat([t[0] for t in p], 0)  # (n_maps, 250, 250)
+                return torch.stack([t[0] for t in p], 0)  # (n_maps, C, 250, 250)
 
             jobs = []
             for rev, owner in ((False, 0), (True, rev_rank)):
@@ -186,7 +190,7 @@ class ShardedForward:
             # independent chains on separate CUDA streams: each decoder conv is a ~20 us launch whose prologue/tail
             # latency the other streams' kernels fill (a single chain runs as one persistent program kernel instead)
             outs = predict.run_concurrent(
-                [(lambda r=r: cascade(r)) if kind == "c" else (lambda r=r: predict.level1_extra(shell, finest(r), mpos, wpos, r)[0, 0])
+                [(lambda r=r: cascade(r)) if kind == "c" else (lambda r=r: predict.level1_extra(shell, finest(r), mpos, wpos, r)[0])
                  for kind, r in jobs], self.device)
             for (kind, rev), o in zip(jobs, outs):
                 (preds if kind == "c" else extras)[rev] = o
@@ -200,13 +204,14 @@ class ShardedForward:
                         buf = torch.empty(shape, dtype=torch.float32, device=self.device)
                         dist.recv(buf, src=src)
                         t_dict[rev] = buf
-                move(preds, True, rev_rank, (n_maps, 250, 250))
+                move(preds, True, rev_rank, (n_maps, self.n_ch, 250, 250))
                 if has_1m:
-                    move(extras, False, x_rank[False], (250, 250))
-                    move(extras, True, x_rank[True], (250, 250))
+                    move(extras, False, x_rank[False], (self.n_ch, 250, 250))
+                    move(extras, True, x_rank[True], (self.n_ch, 250, 250))
             if rank != 0:
                 return None
             if has_1m:
                 for rev in (False, True):
                     preds[rev][5] += extras[rev]
-            return 0.5 * preds[False] + 0.5 * torch.flip(preds[True], [1, 2])
+            out = 0.5 * preds[False] + 0.5 * torch.flip(preds[True], [2, 3])
+            return out[:, 0] if self.n_ch == 1 else out

@@ -155,6 +155,44 @@ def test_net_golden(impl):
     assert isinstance(m2(torch.from_numpy(seq).transpose(1, 2).cuda()), torch.Tensor)
 
 
+@pytest.mark.parametrize("name", ["leukemia_decoder_n2_64", "leukemia_decoder_n6_48", "leukemia_decoder_n6_30_nocoarse",
+                                  "leukemia_decoder_n2_250"])
+def test_leukemia_decoder_golden(name, impl):
+    """orca_leukemia.Decoder(num_2d): num_2d distance / coarse channels in, num_2d maps out."""
+    from orca_b200 import leukemia
+    g = gold(name)
+    n2d, S, B = int(g["num_2d"]), int(g["S"]), int(g["B"])
+    m = native(leukemia.Decoder(n2d), int(g["weight_seed"]))
+    x = randn((B, 128, S), int(g["x_seed"]), 0.5).cuda()
+    distenc = randn((1, n2d, S, S), int(g["d_seed"])).cuda().expand(B, -1, -1, -1)
+    yc = randn((B, n2d, S // 2, S // 2), int(g["y_seed"])).cuda() if bool(g["coarse"]) else None
+    y = m(x, distenc, yc)
+    assert tuple(y.shape) == (B, n2d, S, S)
+    e = relerr(y.cpu().numpy(), g["out"])
+    print(name, impl, "relerr %.2e" % e)
+    assert e <= tol(impl)
+    assert torch.equal(y, y.transpose(2, 3))
+    if yc is not None:  # coarse map as a crop of a larger prediction (channel stride != (S/2)^2), as the cascade passes it
+        big = torch.zeros((B, n2d, S, S), device="cuda")
+        big[:, :, 3:3 + S // 2, 5:5 + S // 2] = yc
+        assert torch.equal(m(x, distenc, big[:, :, 3:3 + S // 2, 5:5 + S // 2]), y)
+
+
+def test_leukemia_decoder_1m_and_net_golden(impl):
+    from orca_b200 import leukemia
+    g = gold("leukemia_decoder1m_n2_40")
+    m = native(leukemia.Decoder_1m(2), int(g["weight_seed"]))
+    y = m(randn((2, 128, 40), int(g["x_seed"]), 0.5).cuda())
+    assert relerr(y.cpu().numpy(), g["out"]) <= tol(impl)
+    g = gold("leukemia_net_n6_24k")
+    m = native(leukemia.Net(6, 8), int(g["weight_seed"]))
+    seq = synthetic.random_sequence(1, int(g["L"]), int(g["seq_seed"]), float(g["n_fraction"]))
+    pred, p1d = m(torch.from_numpy(seq).transpose(1, 2).cuda())
+    assert tuple(pred.shape) == (1, 6, 6, 6)
+    assert relerr(pred.cpu().numpy(), g["out"]) <= tol(impl)
+    assert relerr(p1d.cpu().numpy(), g["out_1d"]) <= tol(impl)
+
+
 def test_background_levels():
     import ctypes
     g = gold("background")
@@ -197,6 +235,21 @@ def test_genomepredict_32mb_golden():
     runner.upload(torch.from_numpy(seq))
     maps = runner.forward(mpos, wpos).cpu().numpy()
     assert max(relerr(maps[i], g["predictions"][i]) for i in range(6)) <= TOL
+
+
+def test_genomepredict_32mb_leukemia_golden():
+    """OrcaLeukemiaA-like shell (2 datasets per map, pooling-only Encoder2, nearest upsample, (2,250,250) normmats)
+    against the unmodified orca_predict.genomepredict on the reference's orca_leukemia classes."""
+    from orca_b200 import models, predict
+    g = gold("genomepredict_32mb_leukemia")
+    shell = models.OrcaLeukemiaA(seed=int(g["shell_seed"]))
+    seq = synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"]))
+    out = predict.genomepredict(seq, "chrS", int(g["mpos"]), int(g["wpos"]), models=[shell])
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    assert out["predictions"][0][0].shape == (2, 250, 250)
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("genomepredict 32 Mb leukemia-A relerr per level (32..1 Mb):", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
 
 
 def test_genomepredict_256mb_driver_golden():

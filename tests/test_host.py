@@ -44,6 +44,23 @@ def test_state_dict_layout_matches_reference_fixture():
     assert len(want["Encoder"]) == 196 and len(want["Decoder"]) == 849
 
 
+def test_leukemia_state_dict_layout_matches_reference_fixture():
+    """orca_leukemia.py classes (num_2d = 2 / 6): same trees, wider combiner / final convs."""
+    from orca_b200 import leukemia
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_keys_leukemia.json")))
+    ctors = {"Decoder2": lambda: leukemia.Decoder(2), "Decoder6": lambda: leukemia.Decoder(6),
+             "Decoder_1m2": lambda: leukemia.Decoder_1m(2), "Net6_8": lambda: leukemia.Net(6, 8),
+             "Encoder": leukemia.Encoder, "Encoder2": leukemia.Encoder2}
+    for name, ctor in ctors.items():
+        got = [[k, list(v.shape)] for k, v in ctor().state_dict().items()]
+        assert got == want[name], name
+    with pytest.raises(ValueError):
+        leukemia.Decoder(9)
+    sh = models.build_shell(leukemia, "leukemia_a", seed=2)
+    assert sorted(sh.denets) == [1, 2, 4, 8, 16, 32] and sh.normmats[4].shape == (2, 250, 250)
+    assert sh.denets[1].num_2d == 2 and sh.denet_1_pt.num_2d == 2 and isinstance(sh.net, modules.Encoder2b)
+
+
 def test_cpu_tensors_are_rejected():
     enc = modules.Encoder()
     with pytest.raises(RuntimeError, match="no CPU path"):

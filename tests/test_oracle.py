@@ -88,6 +88,38 @@ def test_net():
     assert relerr(p1d.numpy(), g["out_1d"]) <= TOL
 
 
+@pytest.mark.parametrize("name", ["leukemia_decoder_n2_64", "leukemia_decoder_n6_48", "leukemia_decoder_n6_30_nocoarse",
+                                  "leukemia_decoder_n2_250"])
+def test_leukemia_decoder(name):
+    """Multi-map decoders of orca_leukemia.py (num_2d = 2 / 6): same oracle functions, wider tensors."""
+    from orca_b200 import leukemia
+    g = gold(name)
+    n2d, S, B = int(g["num_2d"]), int(g["S"]), int(g["B"])
+    sd = sd_for(leukemia.Decoder(n2d), int(g["weight_seed"]))
+    x = randn((B, 128, S), int(g["x_seed"]), 0.5)
+    distenc = randn((1, n2d, S, S), int(g["d_seed"])).expand(B, -1, -1, -1)
+    yc = randn((B, n2d, S // 2, S // 2), int(g["y_seed"])) if bool(g["coarse"]) else None
+    with torch.no_grad():
+        y = oracle.decoder_forward(sd, x, distenc, yc, "nearest")
+    assert tuple(y.shape) == (B, n2d, S, S)
+    assert relerr(y.numpy(), g["out"]) <= TOL
+
+
+def test_leukemia_decoder_1m_and_net():
+    from orca_b200 import leukemia
+    g = gold("leukemia_decoder1m_n2_40")
+    sd = sd_for(leukemia.Decoder_1m(2), int(g["weight_seed"]))
+    with torch.no_grad():
+        y = oracle.decoder_1m_forward(sd, randn((2, 128, 40), int(g["x_seed"]), 0.5))
+    assert relerr(y.numpy(), g["out"]) <= TOL
+    g = gold("leukemia_net_n6_24k")
+    sd = sd_for(leukemia.Net(6, 8), int(g["weight_seed"]))
+    x = torch.from_numpy(synthetic.random_sequence(1, int(g["L"]), int(g["seq_seed"]), float(g["n_fraction"]))).transpose(1, 2)
+    with torch.no_grad():
+        pred, p1d = oracle.net_forward(sd, x, num_1d=8)
+    assert relerr(pred.numpy(), g["out"]) <= TOL and relerr(p1d.numpy(), g["out_1d"]) <= TOL
+
+
 def test_background_levels():
     g = gold("background")
     nm = synthetic.normmat_256mb(chrlen_bins=int(g["chrlen_bins"]))
