@@ -7,6 +7,7 @@
  * what a reference-side binding (ctypes) calls:
  *
  *   orca_b200_encoder_forward     <- Encoder.forward      orca_modules.py:929-980 (layers :811-927)
+ *   orca_b200_encoder_forward_packed  the same + the one-hot feeder, selene_utils2.py:125-128 / :216-230
  *   orca_b200_encoder2_forward    <- Encoder2.forward     orca_modules.py:1151-1169
  *                                    Encoder2b.forward    orca_modules.py:1266-1276
  *                                    Encoder3.forward     orca_modules.py:1388-1406
@@ -154,6 +155,23 @@ int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same forward from PACKED bases, one byte per position -- replaces the reference's
+ * host-side one-hot feeder + fp32 upload (selene_utils2.py:125-128, :216-230; orca_predict.py:324-337:
+ * 16 B/bp over PCIe per strand and model) by 1 B/bp uploaded once.
+ *   bases: (B, L) bytes with BYTE strides (sB, sL).  A byte is either a code 0..4 = A, C, G, T, N or raw
+ *          ASCII as in a FASTA record ('A','C','G','T' in either case; anything else is N).  A/C/G/T become the
+ *          one-hot rows of the reference's ACGT channel order, N becomes 0.25 in all four channels.
+ *   complement != 0 with sL < 0 reads the reverse-complement strand in place: pass bases + (L-1)*|sL|
+ *          (the last position) and a negative sL; codes are complemented (A<->T, C<->G) on the fly.
+ * Everything else as for orca_b200_encoder_forward (x_pos0 / x_len are in positions of the walked strand).
+ */
+int orca_b200_encoder_forward_packed(const orca_b200_module* m, const uint8_t* bases, int64_t B,
+                                     int64_t L, int64_t sB, int64_t sL, int32_t complement,
+                                     int64_t x_pos0, int64_t x_len, float* out, int64_t bin_begin,
+                                     int64_t bin_end, int64_t chunk_bp, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/*
  * Encoder2 / Encoder2b / Encoder3 forward.  x: (B, 128, P) with element strides
  * (sB, sC, sL); P divisible by 32 (Encoder2/2b) or 8 (Encoder3).
  * outs: n_out device pointers, finest -> coarsest, each (B, P >> i, 128) channel-last:
@@ -190,6 +208,11 @@ size_t orca_b200_net_workspace_bytes(const orca_b200_module* m, int64_t B, int64
 int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L,
                           int64_t sB, int64_t sC, int64_t sL, float* out, float* out_1d,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Net.forward from packed bases (see orca_b200_encoder_forward_packed). */
+int orca_b200_net_forward_packed(const orca_b200_module* m, const uint8_t* bases, int64_t B, int64_t L,
+                                 int64_t sB, int64_t sL, int32_t complement, float* out,
+                                 float* out_1d, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Background distance-matrix level (orca_predict.py:724-737 then :693-697):

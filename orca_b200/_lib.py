@@ -45,6 +45,8 @@ SIGNATURES = {
     "orca_b200_encoder_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64, _i64]),
     "orca_b200_encoder_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64,
                                                  _i64, _vp, ctypes.c_size_t, _vp]),
+    "orca_b200_encoder_forward_packed": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _i64, _i64, _vp,
+                                                        _i64, _i64, _i64, _vp, ctypes.c_size_t, _vp]),
     "orca_b200_encoder2_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64]),
     "orca_b200_encoder2_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(_vp),
                                                   ctypes.c_int32, ctypes.c_int32, _vp, ctypes.c_size_t, _vp]),
@@ -54,6 +56,8 @@ SIGNATURES = {
     "orca_b200_net_workspace_bytes": (ctypes.c_size_t, [_vp, _i64, _i64]),
     "orca_b200_net_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp,
                                              ctypes.c_size_t, _vp]),
+    "orca_b200_net_forward_packed": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp, _vp,
+                                                    ctypes.c_size_t, _vp]),
     "orca_b200_background_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp]),
 }
 

@@ -72,12 +72,12 @@ struct ConvCall {
 
 int conv_simt(const ConvLayer& L, const ConvCall& c, cudaStream_t s);
 
-// first encoder layer: Conv1d(4 -> 64, k9) on the caller's strided (B,4,L) input window.
-// x points at sample 0 / position 0; positions [l_begin, l_begin + n) are produced, reading
-// x at [l_begin-4, l_begin+n+4) clipped to [0, L) (zero outside = the conv's own padding).
-int conv_first_simt(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int B,
-                    int64_t Ltot, int64_t l_begin, int64_t n, float* out /*[B][n][64]*/,
-                    cudaStream_t s);
+// first encoder layer: Conv1d(4 -> 64, k9) on the caller's input window (strided fp32 (B,4,L) view or
+// packed bases, seq_in.cuh).  `in` addresses sample 0 / position 0; positions [l_begin, l_begin + n) are
+// produced, reading [l_begin-4, l_begin+n+4) clipped to [0, L) (zero outside = the conv's own padding).
+struct SeqIn;
+int conv_first_simt(const ConvLayer& L, const SeqIn& in, int B, int64_t Ltot, int64_t l_begin, int64_t n,
+                    float* out /*[B][n][64]*/, cudaStream_t s);
 
 // ---- glue kernels -------------------------------------------------------------------------
 // out[b][l][c] = max_{i<p} (a[b][l*p+i][c] + (bb ? bb[b][l*p+i][c] : 0))

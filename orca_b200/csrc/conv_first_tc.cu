@@ -16,6 +16,7 @@
 #include "common.h"
 #include "tc.h"
 #include "tc_device.cuh"
+#include "seq_in.cuh"
 
 namespace orca {
 namespace {
@@ -23,8 +24,7 @@ using namespace tcdev;
 
 constexpr int kTaps = 17, kChunks = 10;  // 68 K-elements padded to 80
 
-__global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict__ x, long long sB, long long sC,
-                                                        long long sL, long long Ltot, long long l_begin, long long n,
+__global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long long Ltot, long long l_begin, long long n,
                                                         int npad, const uint8_t* __restrict__ wimg /*[10][128][16 B]*/,
                                                         const float* __restrict__ bias,
                                                         __nv_bfloat16* __restrict__ out_hi,
@@ -62,24 +62,9 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
 
   // stage the 148 input positions of the tile (l0-8 .. l0+139; zero outside [0, Ltot)) once, coalesced ...
   __shared__ __align__(16) float sX[148][4];
-  {
-    const float* xb = x + (long long)b * sB;
-    for (int i = tid; i < 148; i += 128) {
-      const long long p = l_begin + t0 - 8 + i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p >= 0 && p < Ltot) {
-        const bool vec_ok = ((sL & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb + (sC == -1 ? -3 : 0)) & 15) == 0);
-        if (sC == 1 && vec_ok) {  // channel-last memory: one 16-byte load per position
-          v = __ldg(reinterpret_cast<const float4*>(xb + p * sL));
-        } else if (sC == -1 && vec_ok) {  // reverse-complement walk of channel-last memory: channels stored descending
-          const float4 r = __ldg(reinterpret_cast<const float4*>(xb + p * sL - 3));
-          v = make_float4(r.w, r.z, r.y, r.x);
-        } else {
-          v = make_float4(__ldg(xb + p * sL), __ldg(xb + p * sL + sC), __ldg(xb + p * sL + 2 * sC), __ldg(xb + p * sL + 3 * sC));
-        }
-      }
-      *reinterpret_cast<float4*>(&sX[i][0]) = v;
-    }
+  for (int i = tid; i < 148; i += 128) {  // fp32 view (16 B/bp) or packed bases (1 B/bp): seq_in.cuh
+    const long long p = l_begin + t0 - 8 + i;
+    *reinterpret_cast<float4*>(&sX[i][0]) = (p >= 0 && p < Ltot) ? seq_load(in, b, p) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   // ... then the im2col row of this thread: chunk j = positions (tid + 2j, tid + 2j + 1) of the staged tile
@@ -150,8 +135,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const float* __restrict_
 
 // Exact two-layer evaluation of the 4 positions next to one end of the sequence (see file header).
 // grid (2 ends, nb), 64 threads = output channels.  w1 [9][4][64], w2 [9][64][64] (folded, fp32).
-__global__ void __launch_bounds__(64) lconv1_edge_kernel(const float* __restrict__ x, long long sB, long long sC,
-                                                         long long sL, long long Ltot, long long l_begin, long long n,
+__global__ void __launch_bounds__(64) lconv1_edge_kernel(const SeqIn in, long long Ltot, long long l_begin, long long n,
                                                          int npad, const float* __restrict__ w1, const float* __restrict__ b1,
                                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                                          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
@@ -160,13 +144,14 @@ __global__ void __launch_bounds__(64) lconv1_edge_kernel(const float* __restrict
   const long long p0 = end == 0 ? 0 : Ltot - 8;  // first of the 8 intermediate positions needed
   const long long l0 = end == 0 ? 0 : Ltot - 4;  // first of the 4 output positions
   if (l0 < l_begin || l0 + 4 > l_begin + n) return;  // this window does not own that end
-  const float* xb = x + (long long)b * sB;
   for (int i = 0; i < 8; ++i) {
     float acc = b1[co];
     for (int t = 0; t < 9; ++t) {
       const long long p = p0 + i + t - 4;
       if (p < 0 || p >= Ltot) continue;
-      for (int c = 0; c < 4; ++c) acc = fmaf(__ldg(xb + p * sL + c * sC), w1[(t * 4 + c) * 64 + co], acc);
+      const float4 v4 = seq_load(in, b, p);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      for (int c = 0; c < 4; ++c) acc = fmaf(v[c], w1[(t * 4 + c) * 64 + co], acc);
     }
     y1[i][co] = acc;
   }
@@ -247,8 +232,8 @@ int tc_pack_lconv1(ConvLayer& L0, const float* w1, const float* b1, const float*
   return ORCA_B200_OK;
 }
 
-int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
-              int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s) {
+int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n,
+              TcAct* out, cudaStream_t s) {
   if (!L0.tc_w || !L0.tc_bias || L0.c_in != 4 || L0.c_out != 64 || L1.c_in != 64 || L1.c_out != 64 || out->C != 64 ||
       out->n != n || out->nb != nb) {
     set_error("tc_lconv1: bad layers / geometry");
@@ -265,11 +250,11 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t 
     ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  lconv1_tc_kernel<<<grid, 128, kSmem, s>>>(x, sB, sC, sL, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
+  lconv1_tc_kernel<<<grid, 128, kSmem, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
                                         L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
   ORCA_LAUNCH_OK();
   if (l_begin == 0 || l_begin + n == Ltot) {
-    lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(x, sB, sC, sL, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,
+    lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,
                                                             static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
     ORCA_LAUNCH_OK();
   }

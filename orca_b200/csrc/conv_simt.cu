@@ -7,6 +7,7 @@
 // (tap, 16-channel slice), register-prefetch double buffering through shared memory.
 // Epilogue: folded-BN bias, ReLU, up to two residual adds  --  out = act(conv + b) + res + res2.
 #include "common.h"
+#include "seq_in.cuh"
 
 namespace orca {
 
@@ -205,8 +206,7 @@ int conv_simt(const ConvLayer& L, const ConvCall& c, cudaStream_t s) {
 // in all four channels, selene_utils2.py:216-230), so this is an FMA kernel, not a LUT.
 // Block = 128 positions; thread = 8 consecutive positions x 4 output channels.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, long long sB,
-                                                         long long sC, long long sL, long long Ltot,
+__global__ void __launch_bounds__(256) conv_first_kernel(const SeqIn in, long long Ltot,
                                                          long long l_begin, long long n,
                                                          const float* __restrict__ w,
                                                          const float* __restrict__ bias,
@@ -217,21 +217,11 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * TP;  // first output position of the tile (relative)
-  const float* xb = x + (long long)b * sB;
 
   for (int i = tid; i < 9 * 4 * 64; i += 256) Ws[i] = __ldg(w + i);
-  if (sC == 1 || sC == -1) {  // channel-last memory (or its reverse-complement walk): coalesced
-    for (int idx = tid; idx < NX * 4; idx += 256) {
-      const int j = idx >> 2, c = idx & 3;
-      const long long l = l_begin + t0 - HALO + j;
-      Xs[j][c] = (l >= 0 && l < Ltot) ? __ldg(xb + l * sL + c) : 0.f;
-    }
-  } else {
-    for (int idx = tid; idx < NX * 4; idx += 256) {
-      const int c = idx / NX, j = idx - c * NX;
-      const long long l = l_begin + t0 - HALO + j;
-      Xs[j][c] = (l >= 0 && l < Ltot) ? __ldg(xb + l * sL + c * sC) : 0.f;
-    }
+  for (int j = tid; j < NX; j += 256) {  // one position per thread: fp32 view or packed bases (seq_in.cuh)
+    const long long l = l_begin + t0 - HALO + j;
+    *reinterpret_cast<float4*>(&Xs[j][0]) = (l >= 0 && l < Ltot) ? seq_load(in, b, l) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
 
@@ -266,15 +256,15 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   }
 }
 
-int conv_first_simt(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int B,
-                    int64_t Ltot, int64_t l_begin, int64_t n, float* out, cudaStream_t s) {
+int conv_first_simt(const ConvLayer& L, const SeqIn& in, int B, int64_t Ltot, int64_t l_begin, int64_t n, float* out,
+                    cudaStream_t s) {
   if (L.c_in != 4 || L.c_out != 64 || L.kh != 1 || L.kw != 9) {
     set_error("conv_first_simt: layer is not Conv1d(4,64,k=9)");
     return ORCA_B200_EINVAL;
   }
   if (n <= 0) return ORCA_B200_OK;
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)B), block(256);
-  conv_first_kernel<<<grid, block, 0, s>>>(x, sB, sC, sL, Ltot, l_begin, n, L.w, L.b, out);
+  conv_first_kernel<<<grid, block, 0, s>>>(in, Ltot, l_begin, n, L.w, L.b, out);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }

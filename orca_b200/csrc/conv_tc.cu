@@ -30,6 +30,7 @@
 #include "common.h"
 #include "tc.h"
 #include "tc_device.cuh"
+#include "seq_in.cuh"
 
 namespace orca {
 
@@ -340,8 +341,7 @@ int launch_tc(const TcKArgs& a, int sms, cudaStream_t s) {
 }
 
 // ---- first layer (4 -> 64) writing chunk planes; pool-5 on planes ---------------------------------
-__global__ void __launch_bounds__(256) conv_first_planes_kernel(const float* __restrict__ x, long long sB, long long sC,
-                                                                long long sL, long long Ltot, long long l_begin,
+__global__ void __launch_bounds__(256) conv_first_planes_kernel(const SeqIn in, long long Ltot, long long l_begin,
                                                                 long long n, int npad, const float* __restrict__ w,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ out_hi,
@@ -354,20 +354,10 @@ __global__ void __launch_bounds__(256) conv_first_planes_kernel(const float* __r
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * TP;
-  const float* xb = x + (long long)b * sB;
   for (int i = tid; i < 9 * 4 * 64; i += 256) Ws[i] = __ldg(w + i);
-  if (sC == 1 || sC == -1) {
-    for (int idx = tid; idx < NX * 4; idx += 256) {
-      const int j = idx >> 2, c = idx & 3;
-      const long long l = l_begin + t0 - HALO + j;
-      Xs[j][c] = (l >= 0 && l < Ltot) ? __ldg(xb + l * sL + c * sC) : 0.f;
-    }
-  } else {
-    for (int idx = tid; idx < NX * 4; idx += 256) {
-      const int c = idx / NX, j = idx - c * NX;
-      const long long l = l_begin + t0 - HALO + j;
-      Xs[j][c] = (l >= 0 && l < Ltot) ? __ldg(xb + l * sL + c * sC) : 0.f;
-    }
+  for (int j = tid; j < NX; j += 256) {  // one position per thread: fp32 view or packed bases (seq_in.cuh)
+    const long long l = l_begin + t0 - HALO + j;
+    *reinterpret_cast<float4*>(&Xs[j][0]) = (l >= 0 && l < Ltot) ? seq_load(in, b, l) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   const int cg = tid & 15, pgp = tid >> 4;
@@ -559,11 +549,11 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
   }
 }
 
-int tc_conv_first(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb, int64_t Ltot,
-                  int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s) {
+int tc_conv_first(const ConvLayer& L, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out,
+                  cudaStream_t s) {
   if (L.c_in != 4 || L.c_out != 64 || out->C != 64 || out->n != n || out->nb != nb) { set_error("tc_conv_first: bad geometry"); return ORCA_B200_EINVAL; }
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb), block(256);
-  conv_first_planes_kernel<<<grid, block, 0, s>>>(x, sB, sC, sL, Ltot, l_begin, n, (int)out->npad, L.w, L.b,
+  conv_first_planes_kernel<<<grid, block, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L.w, L.b,
                                                   static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;

@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "tc.h"
+#include "seq_in.cuh"
 
 namespace orca {
 
@@ -173,8 +174,8 @@ struct Arena {
 // ---------------------------------------------------------------------------------------------
 static const int kPool[7] = {1, 4, 4, 5, 5, 5, 2};
 
-static int encoder_window(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
-                          int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
+static int encoder_window(const ConvLayer* L, const SeqIn& x, int nb, int64_t Ltot, int64_t l_begin, int64_t n, float* out7,
+                          Arena& ar, cudaStream_t s) {
   const size_t m = ar.mark();
   const size_t big = (size_t)nb * n * 64;
   float* X0 = ar.f32(big);
@@ -190,7 +191,7 @@ static int encoder_window(const ConvLayer* L, const float* x, int64_t sB, int64_
       ConvCall c;
       c.B = nb; c.H = 1;
       if (k == 0) {
-        ORCA_TRY(conv_first_simt(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, X0, s));
+        ORCA_TRY(conv_first_simt(Lk[0], x, nb, Ltot, l_begin, n, X0, s));
       } else {
         len /= kPool[k];
         c.W = (int)len; c.in = Pb; c.in_ld = Lk[0].c_in; c.out = X0; c.out_ld = C;
@@ -241,8 +242,8 @@ static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res,
 }
 #define tc_conv1d tc_conv1d_prof
 
-static int encoder_window_tc(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
-                             int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
+static int encoder_window_tc(const ConvLayer* L, const SeqIn& x, int nb, int64_t Ltot, int64_t l_begin, int64_t n,
+                             float* out7, Arena& ar, cudaStream_t s) {
   const size_t m = ar.mark();
   const size_t big = 2 * tc_plane_bytes(nb, 64, n);  // stage 1 is the largest tensor of every stage
   void* X[3] = {ar.raw(big), ar.raw(big), ar.raw(big)};
@@ -257,10 +258,10 @@ static int encoder_window_tc(const ConvLayer* L, const float* x, int64_t sB, int
       TcAct t0 = tc_make(X[0], nb, C, len), t1 = tc_make(X[1], nb, C, len), t2 = tc_make(X[2], nb, C, len);
       if (k == 0 && Lk[0].tc_w) {
         // lconv1 (two linear convs) as ONE composed k=17 tensor-core conv straight from the input (conv_first_tc.cu)
-        ORCA_TRY(tc_lconv1(Lk[0], Lk[1], x, sB, sC, sL, nb, Ltot, l_begin, n, &t1, s));
+        ORCA_TRY(tc_lconv1(Lk[0], Lk[1], x, nb, Ltot, l_begin, n, &t1, s));
       } else {
         if (k == 0) {
-          ORCA_TRY(tc_conv_first(Lk[0], x, sB, sC, sL, nb, Ltot, l_begin, n, &t0, s));
+          ORCA_TRY(tc_conv_first(Lk[0], x, nb, Ltot, l_begin, n, &t0, s));
         } else {
           ORCA_TRY(tc_conv1d(Lk[0], in, nullptr, &t0, nullptr, 1, 0, s));
         }
@@ -294,18 +295,25 @@ static bool use_tc_encoder(const ConvLayer* L) {
   return true;
 }
 
-static int encoder_window_any(const ConvLayer* L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
-                              int64_t Ltot, int64_t l_begin, int64_t n, float* out7, Arena& ar, cudaStream_t s) {
-  if (use_tc_encoder(L)) return encoder_window_tc(L, x, sB, sC, sL, nb, Ltot, l_begin, n, out7, ar, s);
-  return encoder_window(L, x, sB, sC, sL, nb, Ltot, l_begin, n, out7, ar, s);
+static int encoder_window_any(const ConvLayer* L, const SeqIn& x, int nb, int64_t Ltot, int64_t l_begin, int64_t n,
+                              float* out7, Arena& ar, cudaStream_t s) {
+  if (use_tc_encoder(L)) return encoder_window_tc(L, x, nb, Ltot, l_begin, n, out7, ar, s);
+  return encoder_window(L, x, nb, Ltot, l_begin, n, out7, ar, s);
+}
+
+// the same input advanced by `b` samples
+static SeqIn seq_at(const SeqIn& x, int64_t b) {
+  SeqIn y = x;
+  if (y.x) y.x += b * y.sB;
+  if (y.bases) y.bases += b * y.sB;
+  return y;
 }
 
 static const int64_t kBin = 4000, kHaloBins = 28;  // x_padding = 112000, orca_modules.py:931-932
 static const int64_t kDefaultChunkBp = 16000000;  // ~13.5 GB of workspace; 2 chunks per 32 Mb strand
 
-static int encoder_run(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
-                       int64_t sL, float* out, int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, Arena& ar,
-                       cudaStream_t s) {
+static int encoder_run(const orca_b200_module* m, const SeqIn& x, int64_t B, int64_t L, float* out, int64_t bin_begin,
+                       int64_t bin_end, int64_t chunk_bp, Arena& ar, cudaStream_t s) {
   const int64_t P = L / kBin;
   if (chunk_bp <= 0) chunk_bp = kDefaultChunkBp;
   int64_t chunk_bins = chunk_bp / kBin;
@@ -325,7 +333,7 @@ static int encoder_run(const orca_b200_module* m, const float* x, int64_t B, int
       const size_t mk = ar.mark();
       float* o7 = ar.f32((size_t)nb * (he - hb) * 128);
       ARENA_OK(ar);
-      ORCA_TRY(encoder_window_any(m->L.data(), x + b0 * sB, sB, sC, sL, nb, L, hb * kBin, n, o7, ar, s));
+      ORCA_TRY(encoder_window_any(m->L.data(), seq_at(x, b0), nb, L, hb * kBin, n, o7, ar, s));
       if (!ar.dry) {
         ORCA_CUDA_OK(cudaMemcpy2DAsync(out + (b0 * P + cb) * 128, (size_t)P * 128 * sizeof(float),
                                        o7 + (cb - hb) * 128, (size_t)(he - hb) * 128 * sizeof(float),
@@ -756,14 +764,14 @@ static int decoder_run(const orca_b200_module* m, const float* x, int64_t B, int
 }
 
 // Net.forward (orca_modules.py:1833-1900): encoder body (monolithic) + Decoder_1m body [+ final_1d]
-static int net_run(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
-                   int64_t sL, float* out, float* out_1d, Arena& ar, cudaStream_t s) {
+static int net_run(const orca_b200_module* m, const SeqIn& x, int64_t B, int64_t L, float* out, float* out_1d, Arena& ar,
+                   cudaStream_t s) {
   const int64_t S = L / kBin;
   const size_t mk = ar.mark();
   float* o7 = ar.f32((size_t)B * S * 128);
   ARENA_OK(ar);
   for (int64_t b = 0; b < B; ++b)
-    ORCA_TRY(encoder_window_any(m->L.data(), x + b * sB, sB, sC, sL, 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
+    ORCA_TRY(encoder_window_any(m->L.data(), seq_at(x, b), 1, L, 0, L, ar.dry ? nullptr : o7 + b * S * 128, ar, s));
   ORCA_TRY(decoder_body_any(m, m->L.data() + ENC_N, true, o7, (int)B, (int)S, Plane4(), Plane4(), out, ar, s));
   if (m->num_1d > 0 && out_1d) {  // final_1d (orca_modules.py:1824-1830, :1852-1853)
     float* h = ar.f32((size_t)B * S * 128);
@@ -947,16 +955,15 @@ static int encoder_args_ok(const orca_b200_module* m, int64_t B, int64_t L, int6
 size_t orca_b200_encoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L, int64_t chunk_bp) {
   if (encoder_args_ok(m, B, L, 0, L / kBin) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
-  encoder_run(m, nullptr, B, L, 0, 0, 0, nullptr, 0, L / kBin, chunk_bp, ar, nullptr);
+  encoder_run(m, SeqIn(), B, L, nullptr, 0, L / kBin, chunk_bp, ar, nullptr);
   return ar.peak + 256;
 }
 
-int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
-                              int64_t sL, int64_t x_pos0, int64_t x_len, float* out, int64_t bin_begin,
-                              int64_t bin_end, int64_t chunk_bp, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+static int encoder_forward_common(const orca_b200_module* m, SeqIn in, int64_t B, int64_t L, int64_t x_pos0, int64_t x_len,
+                                  float* out, int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   ORCA_TRY(encoder_args_ok(m, B, L, bin_begin, bin_end));
-  ORCA_TRY(check_ptr_device(x, "encoder: x"));
+  ORCA_TRY(check_ptr_device(in.bases ? static_cast<const void*>(in.bases) : static_cast<const void*>(in.x), "encoder: x"));
   ORCA_TRY(check_ptr_device(out, "encoder: out"));
   ORCA_TRY(check_ptr_device(workspace, "encoder: workspace"));
   {  // the window x covers must contain everything the requested bins read
@@ -971,9 +978,31 @@ int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t
     }
   }
   Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
-  // virtual base: position l of the sequence lives at x + (l - x_pos0) * sL
-  return encoder_run(m, x - x_pos0 * sL, B, L, sB, sC, sL, out, bin_begin, bin_end, chunk_bp, ar,
-                     static_cast<cudaStream_t>(stream));
+  // virtual base: position l of the sequence lives at base + (l - x_pos0) * sL
+  if (in.x) in.x -= x_pos0 * in.sL;
+  if (in.bases) in.bases -= x_pos0 * in.sL;
+  return encoder_run(m, in, B, L, out, bin_begin, bin_end, chunk_bp, ar, static_cast<cudaStream_t>(stream));
+}
+
+int orca_b200_encoder_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                              int64_t sL, int64_t x_pos0, int64_t x_len, float* out, int64_t bin_begin,
+                              int64_t bin_end, int64_t chunk_bp, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  SeqIn in;
+  in.x = x; in.sB = sB; in.sC = sC; in.sL = sL;
+  return encoder_forward_common(m, in, B, L, x_pos0, x_len, out, bin_begin, bin_end, chunk_bp, workspace, workspace_bytes,
+                                stream);
+}
+
+int orca_b200_encoder_forward_packed(const orca_b200_module* m, const uint8_t* bases, int64_t B, int64_t L, int64_t sB,
+                                     int64_t sL, int32_t complement, int64_t x_pos0, int64_t x_len, float* out,
+                                     int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (sL == 0) { set_error("encoder_forward_packed: position stride is 0"); return ORCA_B200_EINVAL; }
+  SeqIn in;
+  in.bases = bases; in.sB = sB; in.sL = sL; in.complement = complement ? 1 : 0;
+  return encoder_forward_common(m, in, B, L, x_pos0, x_len, out, bin_begin, bin_end, chunk_bp, workspace, workspace_bytes,
+                                stream);
 }
 
 // ---- Encoder2 / 2b / 3 -------------------------------------------------------------------------
@@ -1062,19 +1091,35 @@ size_t orca_b200_net_workspace_bytes(const orca_b200_module* m, int64_t B, int64
   if (net_args_ok(m, B, L) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
   float dummy;
-  net_run(m, nullptr, B, L, 0, 0, 0, nullptr, &dummy, ar, nullptr);
+  net_run(m, SeqIn(), B, L, nullptr, &dummy, ar, nullptr);
   return ar.peak + 256;
 }
 
-int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
-                          int64_t sL, float* out, float* out_1d, void* workspace, size_t workspace_bytes, void* stream) {
+static int net_forward_common(const orca_b200_module* m, const SeqIn& in, int64_t B, int64_t L, float* out, float* out_1d,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   ORCA_TRY(net_args_ok(m, B, L));
-  ORCA_TRY(check_ptr_device(x, "net: x"));
+  ORCA_TRY(check_ptr_device(in.bases ? static_cast<const void*>(in.bases) : static_cast<const void*>(in.x), "net: x"));
   ORCA_TRY(check_ptr_device(out, "net: out"));
   ORCA_TRY(check_ptr_device(workspace, "net: workspace"));
   if (out_1d) ORCA_TRY(check_ptr_device(out_1d, "net: out_1d"));
   Arena ar; ar.base = static_cast<char*>(workspace); ar.cap = workspace_bytes;
-  return net_run(m, x, B, L, sB, sC, sL, out, out_1d, ar, static_cast<cudaStream_t>(stream));
+  return net_run(m, in, B, L, out, out_1d, ar, static_cast<cudaStream_t>(stream));
+}
+
+int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
+                          int64_t sL, float* out, float* out_1d, void* workspace, size_t workspace_bytes, void* stream) {
+  SeqIn in;
+  in.x = x; in.sB = sB; in.sC = sC; in.sL = sL;
+  return net_forward_common(m, in, B, L, out, out_1d, workspace, workspace_bytes, stream);
+}
+
+int orca_b200_net_forward_packed(const orca_b200_module* m, const uint8_t* bases, int64_t B, int64_t L, int64_t sB,
+                                 int64_t sL, int32_t complement, float* out, float* out_1d, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (sL == 0) { set_error("net_forward_packed: position stride is 0"); return ORCA_B200_EINVAL; }
+  SeqIn in;
+  in.bases = bases; in.sB = sB; in.sL = sL; in.complement = complement ? 1 : 0;
+  return net_forward_common(m, in, B, L, out, out_1d, workspace, workspace_bytes, stream);
 }
 
 // ---- profiling -------------------------------------------------------------------------------

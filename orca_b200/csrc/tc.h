@@ -28,15 +28,15 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
 // nearest x2 upsample / channel-last fp32 -> planes, on chunk planes (U-net glue)
 int tc_upsample2_planes(const TcAct& in, TcAct* out, cudaStream_t s);
 int tc_from_channel_last(const float* xcl /*[nb][n][C]*/, TcAct* out, cudaStream_t s);
-int tc_conv_first(const ConvLayer& L, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb, int64_t Ltot,
-                  int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s);
+int tc_conv_first(const ConvLayer& L, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out,
+                  cudaStream_t s);
 int tc_pool_planes(const TcAct& in, TcAct* out, int p, cudaStream_t s);
 // lconv1 (Conv 4->64, BN, Conv 64->64, BN: no nonlinearity) composed into ONE k=17 tensor-core conv
 // (conv_first_tc.cu); L0/L1 = lconv1[0], lconv1[1] (their fp32 weights are used for the sequence-end fix).
 int tc_pack_lconv1(ConvLayer& L0, const float* w1, const float* b1, const float* w2, const float* b2,
                    std::vector<void*>& allocs);
-int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const float* x, int64_t sB, int64_t sC, int64_t sL, int nb,
-              int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out, cudaStream_t s);
+int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n,
+              TcAct* out, cudaStream_t s);
 
 // ---- 2D: (nb, C, S, S) map as hi/lo[nb][C/8][plane_rows][8]; pixel (y, x) at row y*Wp + 64 + x with
 // Wp = S + 128 (64 zero pixels on each side of every image row); pad pixels must stay zero.

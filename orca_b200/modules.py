@@ -186,11 +186,11 @@ class _NativeModule(nn.Module):
         return handle
 
 
-def _require_cuda(name, t):
+def _require_cuda(name, t, dtypes=(torch.float32,)):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError("orca_b200.%s: expected a CUDA tensor (there is no CPU path)" % name)
-    if t.dtype != torch.float32:
-        raise RuntimeError("orca_b200.%s: expected float32, got %s" % (name, t.dtype))
+    if t.dtype not in dtypes:
+        raise RuntimeError("orca_b200.%s: expected %s, got %s" % (name, " or ".join(str(d) for d in dtypes), t.dtype))
 
 
 def _workspace(nbytes, device):
@@ -234,13 +234,15 @@ class Encoder(_NativeModule):
             (B, L/4000, 128) channel-last buffer to fill.
         window=(pos0, L_total): x holds only forward-strand positions [pos0, pos0 + x.size(2)) of a
             sequence of L_total bp (a shard uploads its slice plus the 112 kb halo, not the whole input).
+        x may also be PACKED bases: a uint8 (B, L) tensor of codes 0..4 / raw ASCII (orca_b200.feeder), 1 B/bp.
         """
-        _require_cuda("Encoder.forward", x)
-        pos0, L = (0, x.size(2)) if window is None else window
-        n = x.size(2)
-        if x.dim() != 3 or x.size(1) != 4 or L % 4000 != 0 or L == 0 or n == 0:
-            raise RuntimeError("Encoder.forward: expected (B, 4, L) with L a positive multiple of 4000, got %s"
-                               % (tuple(x.shape),))
+        _require_cuda("Encoder.forward", x, (torch.float32, torch.uint8))
+        packed = x.dtype == torch.uint8
+        n = x.size(-1)
+        pos0, L = (0, n) if window is None else window
+        if (x.dim() != 2 if packed else (x.dim() != 3 or x.size(1) != 4)) or L % 4000 != 0 or L == 0 or n == 0:
+            raise RuntimeError("Encoder.forward: expected float32 (B, 4, L) or packed uint8 (B, L) with L a positive "
+                               "multiple of 4000, got %s %s" % (x.dtype, tuple(x.shape)))
         B = x.shape[0]
         P = L // 4000
         dev = x.device
@@ -253,8 +255,18 @@ class Encoder(_NativeModule):
                 raise RuntimeError("Encoder.forward: out must be a contiguous (B, L/4000, 128) tensor")
             b0, b1 = (0, P) if bin_range is None else bin_range
             ws = _workspace(lib.orca_b200_encoder_workspace_bytes(h, B, L, self.chunk_bp), dev)
-            sB, sC, sL = x.stride()
             xp = x.data_ptr()
+            if packed:
+                sB, sL = x.stride()
+                if reverse_complement:  # walk the same bytes backwards, complementing the codes on the fly
+                    xp += (n - 1) * sL
+                    sL = -sL
+                    pos0 = L - (pos0 + n)
+                _lib.check(lib.orca_b200_encoder_forward_packed(h, ctypes.c_void_p(xp), B, L, sB, sL,
+                                                                1 if reverse_complement else 0, pos0, n, _ptr(out), b0, b1,
+                                                                self.chunk_bp, _ptr(ws), ws.numel(), _stream(dev)))
+                return out.transpose(1, 2)
+            sB, sC, sL = x.stride()
             if reverse_complement:
                 xp += 4 * (3 * sC + (n - 1) * sL)
                 sC, sL = -sC, -sL
@@ -449,11 +461,13 @@ class Net(_NativeModule):
         return int(self.num_1d) if self.num_1d else 0
 
     def forward(self, x):
-        _require_cuda("Net.forward", x)
-        if x.dim() != 3 or x.size(1) != 4 or x.size(2) % 4000 != 0 or x.size(2) == 0:
-            raise RuntimeError("Net.forward: expected (B, 4, L) with L a positive multiple of 4000, got %s"
-                               % (tuple(x.shape),))
-        B, _, L = x.shape
+        """x: float32 (B, 4, L) as the reference takes it, or packed uint8 (B, L) bases (orca_b200.feeder)."""
+        _require_cuda("Net.forward", x, (torch.float32, torch.uint8))
+        packed = x.dtype == torch.uint8
+        if (x.dim() != 2 if packed else (x.dim() != 3 or x.size(1) != 4)) or x.size(-1) % 4000 != 0 or x.size(-1) == 0:
+            raise RuntimeError("Net.forward: expected float32 (B, 4, L) or packed uint8 (B, L) with L a positive "
+                               "multiple of 4000, got %s %s" % (x.dtype, tuple(x.shape)))
+        B, L = x.shape[0], x.shape[-1]
         S = L // 4000
         dev = x.device
         h = self.native_handle(dev)
@@ -462,8 +476,12 @@ class Net(_NativeModule):
             out = torch.empty((B, self.num_2d, S, S), dtype=torch.float32, device=dev)
             out1d = torch.empty((B, self.num_1d, S), dtype=torch.float32, device=dev) if self.num_1d else None
             ws = _workspace(lib.orca_b200_net_workspace_bytes(h, B, L), dev)
-            _lib.check(lib.orca_b200_net_forward(h, _ptr(x), B, L, x.stride(0), x.stride(1), x.stride(2),
-                                                 _ptr(out), None if out1d is None else _ptr(out1d),
-                                                 _ptr(ws), ws.numel(), _stream(dev)))
+            o1 = None if out1d is None else _ptr(out1d)
+            if packed:
+                _lib.check(lib.orca_b200_net_forward_packed(h, _ptr(x), B, L, x.stride(0), x.stride(1), 0, _ptr(out), o1,
+                                                            _ptr(ws), ws.numel(), _stream(dev)))
+            else:
+                _lib.check(lib.orca_b200_net_forward(h, _ptr(x), B, L, x.stride(0), x.stride(1), x.stride(2),
+                                                     _ptr(out), o1, _ptr(ws), ws.numel(), _stream(dev)))
         # reference: `if self.num_1d: return cur, output1d else: return cur`  (:1897-1900)
         return (out, out1d) if self.num_1d else out

@@ -65,12 +65,16 @@ class ShardedForward:
         self.chrlen = chrlen
 
     def upload(self, seq_host):
-        """seq_host: (1, L, 4) float32 CPU tensor (pinned for full-speed copies); uploads this rank's window.
+        """seq_host: (1, L, 4) float32 CPU tensor, or packed bases as a (1, L) uint8 CPU tensor (orca_b200.feeder;
+        16x fewer bytes over PCIe) -- pinned for full-speed copies; uploads this rank's window.
 
         On CUDA the window goes up in `self.pieces` pieces on a copy stream: the forward-strand encoder starts on
         the first range of bins as soon as piece 1 (those bins + halo) has landed, while the rest is in flight."""
-        sl = seq_host[:, self.s0:self.s1, :]
-        self.h2d_bytes = sl.numel() * 4
+        packed = seq_host.dtype == torch.uint8
+        if packed and seq_host.dim() != 2:
+            raise ValueError("packed sequence must be a (1, L) uint8 tensor")
+        sl = seq_host[:, self.s0:self.s1]
+        self.h2d_bytes = sl.numel() * sl.element_size()
         self._ready = None
         if self.device.type != "cuda":
             self.window = sl.to(self.device)
@@ -84,8 +88,8 @@ class ShardedForward:
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        if self.window is None or self.window.shape[1] != n:
-            self.window = torch.empty((1, n, 4), dtype=torch.float32, device=self.device)
+        if self.window is None or self.window.shape[1] != n or self.window.dtype != sl.dtype:
+            self.window = torch.empty((1, n) if packed else (1, n, 4), dtype=sl.dtype, device=self.device)
         cs = self._copy_stream
         cs.wait_stream(main)  # earlier kernels may still be reading the previous contents
         events, lo = [], 0
@@ -105,7 +109,7 @@ class ShardedForward:
         enc = torch.empty((1, self.P, 128), dtype=torch.float32, device=self.device)
         bins = (self.P - self.b1, self.P - self.b0) if reverse else (self.b0, self.b1)
         kw = dict(out=enc, reverse_complement=reverse, window=(self.s0, self.L))
-        x = self.window.transpose(1, 2)
+        x = self.window if self.window.dtype == torch.uint8 else self.window.transpose(1, 2)
         ready, self._ready = (self._ready, None) if not reverse else (None, self._ready)
         if ready is not None and len(ready) > 1:  # first use after a staged upload (forward strand)
             main = torch.cuda.current_stream(self.device)

@@ -19,7 +19,7 @@ modules keep the reference signatures; this file is the fast path, not a require
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, feeder
 
 
 def _device_of(model):
@@ -28,8 +28,25 @@ def _device_of(model):
     raise RuntimeError("model has no parameters")
 
 
+def is_packed(sequence):
+    """Packed-base input (orca_b200.feeder): text, bytes, or a uint8 (L,) / (B, L) array or tensor."""
+    if isinstance(sequence, (str, bytes, bytearray, memoryview)):
+        return True
+    return getattr(sequence, "dtype", None) in (np.uint8, torch.uint8)
+
+
 def _to_device_sequence(sequence, device):
-    """(B, L, 4) float32 host array (or tensor) -> device tensor, one upload."""
+    """One upload: (B, L, 4) float32 host array / tensor as the reference takes it (16 B/bp), or packed bases
+    (str / bytes / uint8 (L,) or (B, L); codes 0..4 or ASCII, 1 B/bp) -> device tensor."""
+    if is_packed(sequence):
+        if not isinstance(sequence, torch.Tensor):
+            sequence = torch.from_numpy(np.ascontiguousarray(feeder.as_bases(sequence)))
+        t = sequence.contiguous()
+        if t.dim() == 1:
+            t = t[None]
+        if t.dim() != 2:
+            raise ValueError("packed sequence must be (L,) or (B, L), got %s" % (tuple(t.shape),))
+        return t.to(device, non_blocking=True)
     if isinstance(sequence, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(sequence, dtype=np.float32))
     else:
@@ -93,8 +110,9 @@ def run_concurrent(jobs, device):
 
 
 def encode_strand(model, seq_dev, reverse):
-    """net0 on one strand of the uploaded (B, L, 4) tensor."""
-    return model.net0(seq_dev.transpose(1, 2), reverse_complement=reverse)
+    """net0 on one strand of the uploaded tensor: float32 (B, L, 4) or packed uint8 (B, L)."""
+    x = seq_dev if seq_dev.dtype == torch.uint8 else seq_dev.transpose(1, 2)
+    return model.net0(x, reverse_complement=reverse)
 
 
 def cascade_starts_32mb(mpos, wpos, reverse):

@@ -83,6 +83,42 @@ def test_encoder_layouts_and_chunks(impl):
     assert torch.equal(part[:, :, 30:90], a[:, :, 30:90])
 
 
+def test_packed_bases_equal_onehot_input(impl):
+    """the encoder fed with 1 B/bp packed bases (codes or raw ASCII, forward and
+    reverse-complement strand, whole sequence or a shard window) is BIT-identical to the fp32 one-hot path."""
+    from orca_b200 import feeder
+    m = native(modules.Encoder(), 5)
+    L = 480000
+    seq = synthetic.random_sequence(2, L, 9, 0.02)
+    codes = feeder.from_onehot(seq)
+    ascii_ = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
+    ascii_[0, ::7] += 32  # some lower-case bases
+    xf = torch.from_numpy(seq).cuda().transpose(1, 2)
+    for rc in (False, True):
+        want = m(xf, reverse_complement=rc)
+        for packed in (codes, ascii_):
+            got = m(torch.from_numpy(packed).cuda(), reverse_complement=rc)
+            assert torch.equal(got, want), (impl, rc)
+    # a shard: only a window of the forward strand is resident (orca_b200.parallel)
+    pos0, pos1 = 80000, 400000
+    part_f = m(xf[:, :, pos0:pos1], bin_range=(50, 70), window=(pos0, L))
+    part_p = m(torch.from_numpy(codes[:, pos0:pos1]).cuda(), bin_range=(50, 70), window=(pos0, L))
+    assert torch.equal(part_p[:, :, 50:70], part_f[:, :, 50:70])
+    part_f = m(xf[:, :, pos0:pos1], bin_range=(50, 70), window=(pos0, L), reverse_complement=True)
+    part_p = m(torch.from_numpy(codes[:, pos0:pos1]).cuda(), bin_range=(50, 70), window=(pos0, L), reverse_complement=True)
+    assert torch.equal(part_p[:, :, 50:70], part_f[:, :, 50:70])
+    # and against the oracle on the reference-format array the codes stand for
+    with torch.no_grad():
+        ref = oracle.encoder_forward(synthetic.fill_state_dict(m.state_dict(), 5), torch.from_numpy(feeder.to_onehot(codes)).transpose(1, 2))
+    assert relerr(m(torch.from_numpy(codes).cuda()).cpu().numpy(), ref.numpy()) <= tol(impl)
+    with pytest.raises(RuntimeError):
+        m(torch.from_numpy(codes))  # CPU tensor
+    # Net (Orca-1Mb) takes packed windows too
+    net = native(modules.Net(), 17)
+    s1 = synthetic.random_sequence(2, 48000, 104, 0.01)
+    assert torch.equal(net(torch.from_numpy(feeder.from_onehot(s1)).cuda()), net(torch.from_numpy(s1).transpose(1, 2).cuda()))
+
+
 @pytest.mark.parametrize("name,cls", [("encoder2_p256", modules.Encoder2), ("encoder3_p64", modules.Encoder3),
                                       ("encoder2b_p64", modules.Encoder2b)])
 def test_unets_golden(name, cls, impl):
@@ -235,6 +271,14 @@ def test_genomepredict_32mb_golden():
     runner.upload(torch.from_numpy(seq))
     maps = runner.forward(mpos, wpos).cpu().numpy()
     assert max(relerr(maps[i], g["predictions"][i]) for i in range(6)) <= TOL
+    # packed-base feeder (1 B/bp): identical maps from both drivers
+    from orca_b200 import feeder
+    codes = feeder.from_onehot(seq)
+    out_p = predict.genomepredict(codes, "chrS", mpos, wpos, models=[shell])
+    assert all(np.array_equal(a, b) for a, b in zip(out_p["predictions"][0], out["predictions"][0]))
+    runner.upload(torch.from_numpy(codes))
+    assert runner.h2d_bytes == 32_000_000
+    assert np.array_equal(runner.forward(mpos, wpos).cpu().numpy(), maps)
 
 
 def test_genomepredict_32mb_leukemia_golden():

@@ -61,6 +61,28 @@ def test_leukemia_state_dict_layout_matches_reference_fixture():
     assert sh.denets[1].num_2d == 2 and sh.denet_1_pt.num_2d == 2 and isinstance(sh.net, modules.Encoder2b)
 
 
+def test_packed_feeder_matches_reference_encoding():
+    """orca_b200.feeder: packed codes / ASCII <-> the reference's one-hot rows (selene_utils2.py:216-230 semantics:
+    ACGT one-hot, everything else 0.25), and the strand flip of orca_predict.py:324-329 on packed codes."""
+    from orca_b200 import feeder
+    seq = synthetic.random_sequence(2, 5000, 7, 0.03)
+    codes = feeder.from_onehot(seq)
+    assert codes.dtype == np.uint8 and codes.shape == (2, 5000) and set(np.unique(codes)) == {0, 1, 2, 3, 4}
+    assert np.array_equal(feeder.to_onehot(codes), seq)
+    text = "ACGTNacgtnRYKM-*"
+    want = np.array([0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 4, 4, 4, 4, 4, 4], dtype=np.uint8)
+    assert np.array_equal(feeder.codes(text), want)
+    assert np.array_equal(feeder.codes(text.encode()), want)
+    assert np.array_equal(feeder.as_bases(text), np.frombuffer(text.encode(), dtype=np.uint8))  # ASCII passes through
+    assert np.array_equal(feeder.to_onehot(feeder.reverse_complement(codes)), seq[:, ::-1, ::-1])
+    bad = seq.copy()
+    bad[0, 3] = [0.5, 0.5, 0.0, 0.0]
+    with pytest.raises(ValueError):
+        feeder.from_onehot(bad)
+    with pytest.raises(TypeError):
+        feeder.as_bases(np.zeros(4, dtype=np.int64))
+
+
 def test_cpu_tensors_are_rejected():
     enc = modules.Encoder()
     with pytest.raises(RuntimeError, match="no CPU path"):
