@@ -16,6 +16,8 @@
  *   orca_b200_net_forward         <- Net.forward          orca_modules.py:1833-1900
  *   orca_b200_background_forward  <- block-nanmean + log of the caller's background matrix,
  *                                    orca_predict.py:693-697 and :724-737
+ *   orca_b200_background_assemble <- the background matrix of a multi-region input,
+ *                                    orca_predict._retrieve_multi, orca_predict.py:936-965
  *
  * Conventions
  *   - plain C types only; every tensor is a raw DEVICE pointer to fp32 unless stated
@@ -224,6 +226,29 @@ int orca_b200_net_forward_packed(const orca_b200_module* m, const uint8_t* bases
  */
 int orca_b200_background_forward(const double* normmat, int64_t n, int64_t r0, int64_t f,
                                  int64_t S, int32_t flip, float* out, void* stream);
+
+/*
+ * Background matrix of a multi-region 256 Mb input, assembled on the device -- replaces the normmat branch of
+ * orca_predict._retrieve_multi (orca_predict.py:936-965), which builds the (8000, 8000) float64 matrix with numpy
+ * on the host (and the caller then uploads 512 MB):
+ *   block(a, b) = cis[(|acoor[:, None] - bcoor[None, :]| / binsize).astype(int)]   same chromosome,
+ *                 acoor = np.linspace(start, end, nb + 1)[:-1],  nb = int((end - start) / binsize)
+ *               = trans                                                          different chromosomes
+ *   rows of a reverse-strand region a and columns of a reverse-strand region b are reversed.
+ * regions: HOST array; chrom is any integer id (equal ids = same chromosome).  cis: DEVICE float64 curve of
+ * n_cis entries (may hold NaN pads, orca_models.py:626-633).  out: DEVICE (n, n) float64 row-major with
+ * n = orca_b200_background_bins(...).  workspace: DEVICE scratch of at least 12*n + 512 bytes.
+ * The call synchronises `stream` once (a 12*n-byte table upload) before the fill kernel is enqueued.
+ */
+typedef struct orca_b200_region {
+  int32_t chrom;
+  int32_t reverse; /* 1 for a '-' strand region */
+  int64_t start, end;
+} orca_b200_region;
+int64_t orca_b200_background_bins(const orca_b200_region* regions, int32_t n_regions, int64_t binsize);
+int orca_b200_background_assemble(const orca_b200_region* regions, int32_t n_regions, const double* cis,
+                                  int64_t n_cis, double trans, int64_t binsize, double* out, int64_t n,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -225,6 +225,27 @@ def main():
             print("background ok")
             save("background", chrlen_bins=6000, **outs)
 
+        # ---------------- multi-region background assembly (orca_predict._retrieve_multi, :936-965) ----------------
+        if want("background_assemble"):
+            class FakeGenome:  # only the sequence branch touches the genome; its output is discarded here
+                def get_encoding_from_coords(self, chrom, start, end, strand="+"):
+                    return np.zeros((4, 4), dtype=np.float32)
+
+            class Bg:
+                pass
+            bg = Bg()
+            bg.background_cis, bg.background_trans = models._background_256mb(None, "h1esc")
+            regions = [("chr1", 0, 3200000, "+"), ("chr1", 8000000, 9600000, "-"), ("chr2", 0, 1600000, "+"),
+                       ("chr1", 3216000, 4816000, "+"), ("chr2", 40000000, 40816000, "-")]
+            _, nms = op._retrieve_multi(regions, FakeGenome(), target=False, normmat=[bg])
+            nm = nms[0]
+            no = oracle.assemble_background(regions, bg.background_cis, bg.background_trans)
+            assert nm.shape == no.shape and np.array_equal(nm, no, equal_nan=True)
+            print("background_assemble", nm.shape, "oracle identical")
+            save("background_assemble", normmat=nm, chroms=np.array([r[0] for r in regions]),
+                 starts=np.array([r[1] for r in regions], dtype=np.int64), ends=np.array([r[2] for r in regions], dtype=np.int64),
+                 strands=np.array([r[3] for r in regions]))
+
         # ---------------- genomepredict through the unmodified driver ----------------
         if want("genomepredict_32mb") and args.big:
             t0 = time.time()

@@ -187,6 +187,28 @@ def background_level(normmat, r0, f, size=250, flip=False):
     return torch.flip(d, [2, 3]) if flip else d
 
 
+def assemble_background(regionlist, background_cis, background_trans, binsize=32000):
+    """Normmat branch of orca_predict._retrieve_multi (orca_predict.py:936-965): the background matrix of a
+    multi-region input.  regionlist: [(chrom, start, end, strand), ...]."""
+    rows = []
+    for chrom, start, end, strand in regionlist:
+        b = []
+        for chrom2, start2, end2, strand2 in regionlist:
+            if chrom2 != chrom:
+                b.append(np.full((int((end - start) / binsize), int((end2 - start2) / binsize)), background_trans))
+            else:
+                acoor = np.linspace(start, end, int((end - start) / binsize) + 1)[:-1]
+                bcoor = np.linspace(start2, end2, int((end2 - start2) / binsize) + 1)[:-1]
+                blk = background_cis[(np.abs(acoor[:, None] - bcoor[None, :]) / binsize).astype(int)]
+                if strand == "-":
+                    blk = blk[::-1, :]
+                if strand2 == "-":
+                    blk = blk[:, ::-1]
+                b.append(blk)
+        rows.append(b)
+    return np.vstack([np.hstack(l) for l in rows])
+
+
 # ------------------------------------------------------------------------------------------------
 # Shell-level restatement used to check whole genomepredict passes without the reference tree.
 # ------------------------------------------------------------------------------------------------

@@ -19,6 +19,11 @@ _i64 = ctypes.c_int64
 _vp = ctypes.c_void_p
 
 
+class Region(ctypes.Structure):
+    """struct orca_b200_region"""
+    _fields_ = [("chrom", ctypes.c_int32), ("reverse", ctypes.c_int32), ("start", ctypes.c_int64), ("end", ctypes.c_int64)]
+
+
 class ConvParams(ctypes.Structure):
     """struct orca_b200_conv_params"""
     _fields_ = [("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("kh", ctypes.c_int32),
@@ -59,6 +64,9 @@ SIGNATURES = {
     "orca_b200_net_forward_packed": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp, _vp,
                                                     ctypes.c_size_t, _vp]),
     "orca_b200_background_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp]),
+    "orca_b200_background_bins": (ctypes.c_int64, [ctypes.POINTER(Region), ctypes.c_int32, _i64]),
+    "orca_b200_background_assemble": (ctypes.c_int, [ctypes.POINTER(Region), ctypes.c_int32, _vp, _i64, ctypes.c_double, _i64,
+                                                     _vp, _i64, _vp, ctypes.c_size_t, _vp]),
 }
 
 _lib = None

@@ -371,4 +371,46 @@ int background_level(const double* normmat, int64_t n, int64_t r0, int64_t f, in
   return ORCA_B200_OK;
 }
 
+// ---- background matrix assembly for multi-region inputs (orca_predict.py:936-965, _retrieve_multi) -------
+// out[i][j] = chrom[i] == chrom[j] ? cis[(long long)(|coord[i] - coord[j]| / binsize)] : trans
+// coord[k] / chrom[k]: genomic coordinate and chromosome id of the bin that lands at row/column k (strand flips
+// already applied by the host).  One thread per pair of columns (16-byte stores); the 1-D cis curve stays in L2.
+__global__ void background_assemble_kernel(const double* __restrict__ coord, const int* __restrict__ chrom,
+                                           const double* __restrict__ cis, double trans, double binsize,
+                                           double* __restrict__ out, long long n) {
+  const long long half = (n + 1) / 2;
+  const long long total = n * half;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / half, j = (t - i * half) * 2;
+    const double ci = __ldg(coord + i);
+    const int ki = __ldg(chrom + i);
+    double v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const long long jj = j + e < n ? j + e : n - 1;
+      if (__ldg(chrom + jj) != ki) { v[e] = trans; continue; }
+      const long long d = (long long)__ddiv_rn(fabs(__dsub_rn(ci, __ldg(coord + jj))), binsize);  // .astype(int) truncates
+      v[e] = __ldg(cis + d);
+    }
+    double* o = out + i * n + j;
+    if (j + 1 < n && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
+    } else {
+      o[0] = v[0];
+      if (j + 1 < n) o[1] = v[1];
+    }
+  }
+}
+
+int background_assemble(const double* coord, const int* chrom, const double* cis, double trans, double binsize,
+                        double* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return ORCA_B200_OK;
+  const long long total = n * ((n + 1) / 2);
+  unsigned grid = blocks_for(total, 256);
+  if (grid > 148u * 32u) grid = 148u * 32u;
+  background_assemble_kernel<<<grid, 256, 0, s>>>(coord, chrom, cis, trans, binsize, out, n);
+  ORCA_LAUNCH_OK();
+  return ORCA_B200_OK;
+}
+
 }  // namespace orca

@@ -1166,4 +1166,65 @@ int orca_b200_background_forward(const double* normmat, int64_t n, int64_t r0, i
   return background_level(normmat, n, r0, f, S, flip, out, static_cast<cudaStream_t>(stream));
 }
 
+// Multi-region background matrix (orca_predict.py:936-965).  Per region the reference takes
+//   coor = np.linspace(start, end, nb + 1)[:-1]  (= start + i * ((end - start) / nb) in float64),  nb = int((end - start) / binsize)
+// indexes cis with (|acoor - bcoor| / binsize).astype(int) for region pairs on the same chromosome, fills `trans`
+// otherwise, and reverses the rows / columns of a '-' strand region.  The per-bin coordinate table (strand flips
+// applied) is built here on the host in the same float64 arithmetic; the n x n fill runs on the device.
+int64_t orca_b200_background_bins(const orca_b200_region* regions, int32_t n_regions, int64_t binsize) {
+  if (!regions || n_regions <= 0 || binsize <= 0) { set_error("background_bins: bad arguments"); return ORCA_B200_EINVAL; }
+  int64_t n = 0;
+  for (int r = 0; r < n_regions; ++r) {
+    if (regions[r].end <= regions[r].start) { set_error("background_bins: region %d is empty", r); return ORCA_B200_EINVAL; }
+    n += (int64_t)((double)(regions[r].end - regions[r].start) / (double)binsize);
+  }
+  return n;
+}
+
+int orca_b200_background_assemble(const orca_b200_region* regions, int32_t n_regions, const double* cis, int64_t n_cis,
+                                  double trans, int64_t binsize, double* out, int64_t n, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  const int64_t want = orca_b200_background_bins(regions, n_regions, binsize);
+  if (want < 0) return (int)want;
+  if (want != n) { set_error("background_assemble: regions hold %lld bins, out is %lld x %lld", (long long)want, (long long)n, (long long)n); return ORCA_B200_EINVAL; }
+  ORCA_TRY(check_ptr_device(cis, "background_assemble: cis"));
+  ORCA_TRY(check_ptr_device(out, "background_assemble: out"));
+  ORCA_TRY(check_ptr_device(workspace, "background_assemble: workspace"));
+  const size_t need = (size_t)n * (sizeof(double) + sizeof(int)) + 256;
+  if (workspace_bytes < need) { set_error("background_assemble: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, need); return ORCA_B200_EWORKSPACE; }
+  std::vector<double> coord((size_t)n);
+  std::vector<int> chrom((size_t)n);
+  int64_t k = 0;
+  for (int r = 0; r < n_regions; ++r) {
+    const orca_b200_region& g = regions[r];
+    const int64_t nb = (int64_t)((double)(g.end - g.start) / (double)binsize);
+    const double step = (double)(g.end - g.start) / (double)nb;
+    for (int64_t i = 0; i < nb; ++i) {
+      const int64_t src = g.reverse ? nb - 1 - i : i;
+      volatile double prod = (double)src * step;  // numpy: arange * step, then + start (two roundings, no FMA)
+      coord[(size_t)k] = prod + (double)g.start;
+      chrom[(size_t)k] = g.chrom;
+      ++k;
+    }
+  }
+  // every cis lookup must be inside the curve (numpy would raise IndexError)
+  for (int a = 0; a < n_regions; ++a)
+    for (int b = 0; b < n_regions; ++b) {
+      if (regions[a].chrom != regions[b].chrom) continue;
+      const double far = std::fmax(std::fabs((double)(regions[a].start - regions[b].end)), std::fabs((double)(regions[a].end - regions[b].start)));
+      if ((int64_t)(far / (double)binsize) >= n_cis) {
+        set_error("background_assemble: regions %d and %d are %lld bins apart, the cis curve has %lld entries", a, b,
+                  (long long)(far / (double)binsize), (long long)n_cis);
+        return ORCA_B200_EINVAL;
+      }
+    }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* d_coord = static_cast<double*>(workspace);
+  int* d_chrom = reinterpret_cast<int*>(static_cast<char*>(workspace) + (((size_t)n * sizeof(double) + 255) & ~size_t(255)));
+  ORCA_CUDA_OK(cudaMemcpyAsync(d_coord, coord.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  ORCA_CUDA_OK(cudaMemcpyAsync(d_chrom, chrom.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  ORCA_CUDA_OK(cudaStreamSynchronize(s));  // the host tables go out of scope on return
+  return background_assemble(d_coord, d_chrom, cis, trans, (double)binsize, out, n, s);
+}
+
 }  // extern "C"

@@ -208,9 +208,42 @@ def genomepredict(sequence, mchr, mpos=-1, wpos=-1, models=(), targets=None, ann
     return output
 
 
+def assemble_background(regionlist, background_cis, background_trans, device, binsize=32000):
+    """Background matrix of a multi-region input, built on the device: the normmat branch of
+    orca_predict._retrieve_multi (orca_predict.py:936-965) without the host numpy assembly and the 512 MB upload.
+
+    regionlist: [(chrom, start, end[, strand]), ...]; background_cis / background_trans: the shell's 32 kb curve
+    (NaN-padded, orca_models.py:626-633) and trans constant.  Returns an (n, n) float64 device tensor that
+    genomepredict_256Mb(normmats=[...]) accepts directly."""
+    import ctypes
+    device = torch.device(device)
+    ids = {}
+    regs = (_lib.Region * len(regionlist))()
+    for r, region in zip(regs, regionlist):
+        chrom, start, end = region[:3]
+        strand = region[3] if len(region) > 3 else "+"
+        r.chrom, r.reverse, r.start, r.end = ids.setdefault(chrom, len(ids)), 1 if strand == "-" else 0, int(start), int(end)
+    lib = _lib.lib()
+    n = int(lib.orca_b200_background_bins(regs, len(regs), int(binsize)))
+    if n < 0:
+        _lib.check(n)
+    with torch.cuda.device(device):
+        cis = torch.as_tensor(np.asarray(background_cis, dtype=np.float64)).to(device)
+        out = torch.empty((n, n), dtype=torch.float64, device=device)
+        ws = torch.empty(12 * n + 512, dtype=torch.uint8, device=device)
+        _lib.check(lib.orca_b200_background_assemble(regs, len(regs), cis.data_ptr(), cis.numel(), float(background_trans),
+                                                     int(binsize), out.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return out
+
+
 def prepare_background(normmat, device):
-    """Caller's (n, n) float64 background matrix -> device, NaNs replaced by the minimum (orca_predict.py:668-671)."""
-    t = torch.as_tensor(np.asarray(normmat, dtype=np.float64)).to(device)
+    """Caller's (n, n) float64 background matrix (host array, or a device tensor from assemble_background) -> device,
+    NaNs replaced by the minimum (orca_predict.py:668-671)."""
+    if isinstance(normmat, torch.Tensor):
+        t = normmat.to(device=device, dtype=torch.float64)
+    else:
+        t = torch.as_tensor(np.asarray(normmat, dtype=np.float64)).to(device)
     nan = torch.isnan(t)
     if bool(nan.any()):
         t = torch.where(nan, t[~nan].min(), t)

@@ -240,6 +240,29 @@ def test_background_levels():
         assert relerr(out.cpu().numpy(), g[tag][0, 0]) <= 1e-6
 
 
+def test_background_assemble_golden():
+    """Device assembly of the multi-region background matrix: bit-exact against orca_predict._retrieve_multi
+    (fixture), including reverse-strand regions, a second chromosome and a region that is not a multiple of 32 kb;
+    and at the full 8000 x 8000 size against the oracle's numpy restatement through the level kernel."""
+    from orca_b200 import models, predict
+    g = gold("background_assemble")
+    regions = [(str(c), int(a), int(b), str(s)) for c, a, b, s in zip(g["chroms"], g["starts"], g["ends"], g["strands"])]
+    cis, trans = models._background_256mb(None, "h1esc")
+    nm = predict.assemble_background(regions, cis, trans, "cuda")
+    assert nm.dtype == torch.float64 and tuple(nm.shape) == g["normmat"].shape
+    assert np.array_equal(nm.cpu().numpy(), g["normmat"], equal_nan=True)
+    big = [("chr7", 0, 160_000_000, "+"), ("chr9", 1_000_000, 97_000_000, "-")]
+    ref = oracle.assemble_background(big, cis, trans)
+    got = predict.assemble_background(big, cis, trans, "cuda")
+    assert np.array_equal(got.cpu().numpy(), ref, equal_nan=True)
+    # feeds the level kernel like a host matrix does (NaN pads replaced by the minimum first, orca_predict.py:668-671)
+    a = predict.background_level(predict.prepare_background(got, torch.device("cuda")), 1000, 16)
+    b = predict.background_level(predict.prepare_background(ref, torch.device("cuda")), 1000, 16)
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):  # a lookup beyond the curve (numpy raises IndexError there)
+        predict.assemble_background([("chr1", 0, 400_000_000, "+")], cis, trans, "cuda")
+
+
 def test_errors_are_loud():
     m = native(modules.Encoder(), 1)
     with pytest.raises(RuntimeError):

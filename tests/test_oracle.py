@@ -128,6 +128,16 @@ def test_background_levels():
         assert relerr(d.numpy(), g[tag]) <= 1e-7
 
 
+def test_background_assemble():
+    """Multi-region background matrix (orca_predict._retrieve_multi, :936-965) vs the fixture from the reference."""
+    from orca_b200 import models
+    g = gold("background_assemble")
+    regions = [(str(c), int(a), int(b), str(s)) for c, a, b, s in zip(g["chroms"], g["starts"], g["ends"], g["strands"])]
+    cis, trans = models._background_256mb(None, "h1esc")
+    nm = oracle.assemble_background(regions, cis, trans)
+    assert nm.shape == g["normmat"].shape and np.array_equal(nm, g["normmat"], equal_nan=True)
+
+
 def test_blockwise_equals_monolithic():
     """The reference's 800 kb blocks with 112 kb overlap are exact w.r.t. one monolithic pass
     (receptive field 104,016 bp < 112,000 bp): property used by the chunked / sharded CUDA encoder."""
