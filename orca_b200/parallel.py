@@ -52,6 +52,10 @@ class ShardedForward:
         self._cuts = [self.b0, self.b1]
         self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
+        # how a single GPU runs the two strand cascades: "streams" = four independent chains (2 cascades + 2
+        # Decoder_1m terms) on four CUDA streams, one launch per conv; "batch" = the two strands as the two batch
+        # elements of ONE chain (every decoder call is one persistent program kernel at batch 2)
+        self.cascade_mode = "batch"
         self.h2d_bytes = 0
         # maps per level: 1, or num_2d for the multi-dataset shells of orca_leukemia.py
         denets = getattr(shell, "denets", None) or {}
@@ -182,6 +186,18 @@ class ShardedForward:
                 else:
                     p, _ = predict.cascade_32mb(shell, finest(rev), 1, mpos, wpos, rev, inline_1m=False)
                 return torch.stack([t[0] for t in p], 0)  # (n_maps, C, 250, 250)
+
+            if world == 1 and self.cascade_mode == "batch":
+                lanes = [(finest(False), False), (finest(True), True)]
+                if is256:
+                    if self.background is None:
+                        raise RuntimeError("256 Mb shells need set_background(normmat, chrlen) before forward()")
+                    p, _ = predict.cascade_256mb_lanes(shell, lanes, self.background, self.chrlen, mpos, wpos)
+                else:
+                    p, _ = predict.cascade_32mb_lanes(shell, lanes, mpos, wpos, inline_1m=True)
+                both = torch.stack(p, 0)  # (n_maps, 2 strands, C, 250, 250)
+                out = 0.5 * both[:, 0] + 0.5 * torch.flip(both[:, 1], [2, 3])
+                return out[:, 0] if self.n_ch == 1 else out
 
             jobs = []
             for rev, owner in ((False, 0), (True, rev_rank)):

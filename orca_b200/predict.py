@@ -161,6 +161,39 @@ def cascade_32mb(model, encodings, batch, mpos, wpos, reverse, inline_1m=True):
     return preds, starts[:-1]
 
 
+def _next_index_32mb(level, start, mpos, wpos, reverse):
+    """Crop index of the next zoom level (orca_predict.py:470-497)."""
+    if not reverse:
+        v = np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + start * 4000)) / (4000 * level))
+    else:
+        v = np.ceil(((wpos + 16000000 - start * 4000) - (mpos + level * 1000000 / 4)) / (4000 * level))
+    return int(np.clip(v, 0, 125))
+
+
+def cascade_32mb_lanes(model, lanes, mpos, wpos, inline_1m=True):
+    """Several independent cascades of ONE model (e.g. its two strands) as one batched chain: every decoder call
+    carries one batch element per lane, so the 118 dependent layers of a level are paid once instead of per strand
+    (each lane keeps its own crop windows; the arithmetic per lane is exactly cascade_32mb's).
+
+    lanes: [(encodings {level: (1, 128, P/level)}, reverse), ...].  Returns (preds: list over levels of
+    (n_lanes, C, 250, 250), starts: per-lane start bins)."""
+    n = len(lanes)
+    device = lanes[0][0][1].device
+    starts, sidx, preds = [[0] for _ in lanes], [0] * n, []
+    for j, level in enumerate([32, 16, 8, 4, 2, 1]):
+        distenc = _log_normmat(model, level, device).expand(n, -1, -1, -1)
+        xl = torch.cat([enc[level][:, :, int(st[j] / level):int(st[j] / level) + 250] for (enc, _), st in zip(lanes, starts)], 0)
+        coarse = None if j == 0 else torch.stack([preds[j - 1][i, :, si:si + 125, si:si + 125] for i, si in enumerate(sidx)], 0)
+        pred = model.denets[level].forward(xl, distenc, coarse)
+        if level == 1 and hasattr(model, "denet_1_pt") and inline_1m:
+            pred = pred + model.denet_1_pt.forward(xl)
+        for i, (_, rev) in enumerate(lanes):
+            sidx[i] = _next_index_32mb(level, starts[i][j], mpos, wpos, rev)
+            starts[i].append(starts[i][j] + sidx[i] * level)
+        preds.append(pred)
+    return preds, [st[:-1] for st in starts]
+
+
 def _average_strands(fwd, rev):
     """0.5*fwd + 0.5*rev[::-1, ::-1] for batch element 0 (orca_predict.py:510-523)."""
     out = []
@@ -287,6 +320,35 @@ def cascade_256mb(model, encodings, batch, normmat_dev, chrlen, mpos, wpos, reve
         starts.append(starts[j] + start_index * level // 8)
         preds.append(pred)
     return preds, starts[:-1], ns
+
+
+def cascade_256mb_lanes(model, lanes, normmat_dev, chrlen, mpos, wpos):
+    """cascade_256mb for several lanes (strands) of one model as one batched chain; see cascade_32mb_lanes.
+    Returns (preds: list over levels of (n_lanes, C, 250, 250), per-lane starts)."""
+    n = len(lanes)
+    starts, sidx, preds = [[0] for _ in lanes], [0] * n, []
+    for j, level in enumerate([256, 128, 64, 32]):
+        f = level // 8
+        dist, xs = [], []
+        for (enc, rev), st in zip(lanes, starts):
+            dist.append(background_level(normmat_dev, st[j], f, flip=rev)[0])
+            s = int(st[j] / f)
+            xs.append(enc[level][:, :, s:s + 250])
+        coarse = None if j == 0 else torch.stack([preds[j - 1][i, :, si:si + 125, si:si + 125] for i, si in enumerate(sidx)], 0)
+        pred = model.denets[level].forward(torch.cat(xs, 0), torch.stack(dist, 0), coarse)
+        for i, (_, rev) in enumerate(lanes):
+            if not rev:
+                proposed = (mpos - level * 1000000 / 4) - (wpos - 128000000 + starts[i][j] * 4000 * 8)
+            else:
+                proposed = (mpos - level * 1000000 / 4) - (wpos + 128000000 - starts[i][j] * 4000 * 8 - level * 1000000)
+            if chrlen is not None:
+                bounds = [0 - (wpos - 128000000), chrlen - level * 1000000 / 2 - (wpos - 128000000)]
+                proposed = np.clip(proposed, bounds[0], bounds[1]) if bounds[0] < bounds[1] else bounds[0]
+            si = int(np.clip(np.floor(proposed / (4000 * level)), 0, 125))
+            sidx[i] = 250 - (si + 125) if rev else si
+            starts[i].append(starts[i][j] + sidx[i] * level // 8)
+        preds.append(pred)
+    return preds, [st[:-1] for st in starts]
 
 
 def genomepredict_256Mb(sequence, mchr, normmats, chrlen, mpos=-1, wpos=-1, models=(), targets=None, annotation=None,
