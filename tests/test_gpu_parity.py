@@ -294,6 +294,11 @@ def test_genomepredict_32mb_golden():
     runner.upload(torch.from_numpy(seq))
     maps = runner.forward(mpos, wpos).cpu().numpy()
     assert max(relerr(maps[i], g["predictions"][i]) for i in range(6)) <= TOL
+    # the four-stream schedule (one launch per conv) computes the same maps as the batched-strand chain
+    runner.cascade_mode = "streams"
+    maps_s = runner.forward(mpos, wpos).cpu().numpy()
+    runner.cascade_mode = "batch"
+    assert max(relerr(maps_s[i], maps[i]) for i in range(6)) <= 1e-6
     # packed-base feeder (1 B/bp): identical maps from both drivers
     from orca_b200 import feeder
     codes = feeder.from_onehot(seq)
@@ -394,3 +399,6 @@ def test_sharded_runner_256mb_matches_driver():
     assert maps.shape == (4, 250, 250) and np.isfinite(maps).all()
     for i in range(4):
         assert relerr(maps[i], ref["predictions"][0][i]) <= 1e-6, i
+    runner.cascade_mode = "streams"
+    maps_s = runner.forward(mpos, wpos).cpu().numpy()
+    assert max(relerr(maps_s[i], maps[i]) for i in range(4)) <= 1e-6
