@@ -65,7 +65,8 @@ def _log_normmat(model, level, device):
         cache[key] = torch.log(torch.as_tensor(nm, dtype=torch.float32).to(device))
         # the cached tensor is shared by cascades running on different streams (run_concurrent): make sure it is
         # complete before any other stream can pick it up (one-time cost per model and level)
-        torch.cuda.current_stream(device).synchronize()
+        if torch.device(device).type == "cuda":
+            torch.cuda.current_stream(device).synchronize()
     return cache[key]
 
 

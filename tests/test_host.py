@@ -143,3 +143,58 @@ def test_shard_geometry():
     s0, s1 = parallel.shard_window(32_000_000, 1000, 2000)
     assert s0 == 1000 * 4000 - 116000 and s1 == 2000 * 4000 + 116000
     assert parallel.shard_window(32_000_000, 0, 8000) == (0, 32_000_000)
+
+
+class _FakeDecoder(torch.nn.Module):
+    """Stand-in with Decoder.forward's signature: a cheap deterministic function of all three inputs."""
+
+    def __init__(self, k):
+        super().__init__()
+        self.k = k
+
+    def forward(self, x, distenc, y=None):
+        m = x.mean(1)
+        out = (m[:, :, None] + m[:, None, :])[:, None] * self.k + 0.1 * distenc
+        if y is not None:
+            out = out + torch.nn.functional.interpolate(y, scale_factor=(2, 2), mode="nearest")
+        return out
+
+
+def test_lane_batched_cascades_equal_separate_cascades(monkeypatch):
+    """Host logic of predict.cascade_*_lanes (strands as batch elements of one chain): per-lane crop windows,
+    coarse crops and start bins must equal running each strand's cascade on its own."""
+    import orca_oracle as oracle
+    from orca_b200 import predict
+    rng = np.random.default_rng(0)
+    shell = torch.nn.Module()
+    mats, _ = synthetic.normmats_32mb()
+    shell.normmats = mats
+    dec = {lvl: _FakeDecoder(1.0 + 0.1 * i) for i, lvl in enumerate([1, 2, 4, 8, 16, 32])}
+    shell.denets = dec
+    shell.denet_1_pt = type("D1", (), {"forward": staticmethod(lambda x: (x.mean(1)[:, :, None] * x.mean(1)[:, None, :])[:, None])})()
+    encs = [{lvl: torch.from_numpy(rng.standard_normal((1, 128, 8000 // lvl)).astype(np.float32)) for lvl in [1, 2, 4, 8, 16, 32]}
+            for _ in range(2)]
+    mpos, wpos = 17_300_000, 16_000_000
+    lanes_p, lanes_s = predict.cascade_32mb_lanes(shell, [(encs[0], False), (encs[1], True)], mpos, wpos)
+    for i, rev in enumerate((False, True)):
+        p, st = predict.cascade_32mb(shell, encs[i], 1, mpos, wpos, rev)
+        assert st == lanes_s[i]
+        for a, b in zip(p, lanes_p):
+            assert torch.equal(a[0], b[i])
+    assert lanes_s[0] != lanes_s[1]  # the two strands really zoom into different windows
+    assert lanes_s[0] == predict.cascade_starts_32mb(mpos, wpos, False)
+
+    # 256 Mb analogue; the device background kernel is replaced by the oracle's numpy restatement
+    nm = synthetic.normmat_256mb(chrlen_bins=7000)
+    monkeypatch.setattr(predict, "background_level",
+                        lambda normmat, r0, f, flip=False, size=250: oracle.background_level(normmat, r0, f, size, flip))
+    shell.denets = {lvl: _FakeDecoder(1.0 + 0.1 * i) for i, lvl in enumerate([32, 64, 128, 256])}
+    encs = [{lvl: torch.from_numpy(rng.standard_normal((1, 128, 8000 * 32 // lvl)).astype(np.float32)) for lvl in [32, 64, 128, 256]}
+            for _ in range(2)]
+    mpos, wpos, chrlen = 100_000_000, 128_000_000, 7000 * 32000
+    lanes_p, lanes_s = predict.cascade_256mb_lanes(shell, [(encs[0], False), (encs[1], True)], nm, chrlen, mpos, wpos)
+    for i, rev in enumerate((False, True)):
+        p, st, _ = predict.cascade_256mb(shell, encs[i], 1, nm, chrlen, mpos, wpos, rev)
+        assert st == lanes_s[i]
+        for a, b in zip(p, lanes_p):
+            assert torch.equal(a[0], b[i])
