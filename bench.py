@@ -86,10 +86,17 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------
 # reference algorithm on the host CPU (oracle port; test/baseline infrastructure)
 # ----------------------------------------------------------------------------------------------------
+CPU_BLOCKS = 6   # encoder blocks per CPU sample (of the 40 per strand at 32 Mb)
+CPU_DECODERS = 2  # Decoder calls per CPU sample (of the 6 per strand)
+CPU_SAMPLE = ("%d of 40 encoder blocks per strand (912 kb each incl. the 112 kb halo), Encoder2@8000, %d of 6 Decoder calls, "
+              "Decoder_1m" % (CPU_BLOCKS, CPU_DECODERS))
+
+
 def cpu_sample(threads):
-    """Time a bounded sample of the workload with the oracle port on `threads` host threads and
-    extrapolate to one full step.  Sample: one 800 kb encoder block with its 112 kb halo
-    (orca_modules.py:957-977), Encoder2 on 8000 bins, one Decoder call and one Decoder_1m call."""
+    """Time a bounded sample (~10-20 s of CPU work) of the workload with the oracle port on `threads` host threads
+    and extrapolate to one full step.  Sample: CPU_BLOCKS 800 kb encoder blocks with their 112 kb halo
+    (orca_modules.py:957-977), Encoder2 on 8000 bins, CPU_DECODERS Decoder calls and one Decoder_1m call; returns
+    per-unit seconds (block, Encoder2, Decoder, Decoder_1m)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orca_oracle as oracle
@@ -107,12 +114,16 @@ def cpu_sample(threads):
 
     def one():
         with torch.no_grad():
-            t0 = time.perf_counter(); oracle.encoder_run(sd_e, x)
+            t0 = time.perf_counter()
+            for _ in range(CPU_BLOCKS):
+                oracle.encoder_run(sd_e, x)
             t1 = time.perf_counter(); encs = oracle.encoder2_forward(sd_n, e)
-            t2 = time.perf_counter(); oracle.decoder_forward(sd_d, encs[-1], d, y, "bilinear")
+            t2 = time.perf_counter()
+            for _ in range(CPU_DECODERS):
+                oracle.decoder_forward(sd_d, encs[-1], d, y, "bilinear")
             t3 = time.perf_counter(); oracle.decoder_1m_forward(sd_m, encs[-1])
             t4 = time.perf_counter()
-        return t1 - t0, t2 - t1, t3 - t2, t4 - t3
+        return (t1 - t0) / CPU_BLOCKS, t2 - t1, (t3 - t2) / CPU_DECODERS, t4 - t3
     return one
 
 
@@ -137,8 +148,7 @@ def run_reference(args, rank):
     tb, te, td, tm = acc / args.steps
     full = cpu_extrapolate(tb, te, td, tm)
     value = 2 * SEQ_LEN / full / 1e6
-    sample = ("per step: 1 of 40 encoder blocks (912 kb incl. halo), Encoder2@8000, 1 of 6 Decoder calls, Decoder_1m; "
-              "extrapolated linearly to 2 strands x (40 blocks + Encoder2 + 6 Decoder + Decoder_1m)")
+    sample = ("per step: " + CPU_SAMPLE + "; extrapolated linearly to 2 strands x (40 blocks + Encoder2 + 6 Decoder + Decoder_1m)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -166,6 +176,9 @@ def main():
                     help="32mb = BASELINE configs[1] (default, what the driver runs); 256mb = configs[3], the "
                          "H1esc_256M-like genomepredict_256Mb forward (256 Mb, 4 levels), sequence-sharded the same way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--enc-fp16-stages", type=int, default=-1,
+                    help="leading encoder stages in single-pass fp16 (0 = three-product bf16 everywhere; default: library default, 3)")
+    ap.add_argument("--cascade-mode", default=None, choices=["streams", "batch"])
     ap.add_argument("--chunk-bp", type=int, default=0, help="encoder chunk length in bp (0 = library default)")
     ap.add_argument("--concurrent-strands", action="store_true", help="encode the two strands on two CUDA streams")
     args = ap.parse_args()
@@ -188,6 +201,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_impl(args.kernels)
+    enc16 = _lib.set_encoder_fp16_stages(args.enc_fp16_stages)  # returns the previous (= default) setting
+    if args.enc_fp16_stages >= 0:
+        enc16 = min(args.enc_fp16_stages, 7)
     peaks = load_peaks()
     big = args.workload == "256mb"
     L = 256_000_000 if big else args.seq_len
@@ -201,6 +217,8 @@ def main():
     seq_host = torch.from_numpy(synthetic.random_sequence(1, L, 0)).pin_memory()
     runner = parallel.ShardedForward(shell, L, rank, world, dev)
     runner.concurrent_strands = args.concurrent_strands
+    if args.cascade_mode:
+        runner.cascade_mode = args.cascade_mode
     runner.upload(seq_host)  # device-resident input for the `value` leg
     if big:
         runner.set_background(synthetic.normmat_256mb(chrlen_bins=7500), 7500 * 32000)
@@ -263,7 +281,8 @@ def main():
     # group the per-shape records by kernel: (c_in, c_out, Conv1d|Conv2d, tcgen05|simt); Conv1d records carry dil = 0
     groups = {}
     for r in prof:
-        key = (r["c_in"], r["c_out"], "conv1d_k9" if r["dil"] == 0 else "conv2d_3x3", "tcgen05" if r["tc"] else "simt fp32")
+        key = (r["c_in"], r["c_out"], "conv1d_k9" if r["dil"] == 0 else ("decoder_program" if r["c_in"] < 0 else "conv2d_3x3"),
+               {0: "simt fp32", 1: "tcgen05 bf16x3", 2: "tcgen05 fp16x1"}[r["tc"]])
         grp = groups.setdefault(key, {"ms": 0.0, "launches": 0, "flop": 0.0})
         grp["ms"] += r["ms"]; grp["launches"] += r["launches"]; grp["flop"] += r["flop"]
     roofline = None
@@ -272,12 +291,12 @@ def main():
         dur_ms = dom["ms"] / dom["launches"]
         achieved = dom["flop"] / dom["launches"] / (dur_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        split = 3 if key[3] == "tcgen05" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
+        split = 3 if key[3] == "tcgen05 bf16x3" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
         # DRAM bytes per position from the committed ncu --set full capture (profiles/r01_prof_conv1d.md: 1.024 GB read +
         # 0.978 GB written for 4.224 M positions of the 64->64 kernel = algorithmic 2 x 64 ch x 4 B planes), scaled to
         # this run's positions per launch
         traffic = None
-        if key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05":
+        if key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 bf16x3":
             traffic = 474.0 * dom["flop"] / dom["launches"] / (2 * 9 * 64 * 64)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
@@ -293,10 +312,13 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-                "dtype": "bf16x3 (fp32 operands split hi+lo, 3 tcgen05 products, fp32 accumulate)" if args.kernels != "simt" else "f32",
+                "dtype": ("f32" if args.kernels == "simt" else
+                          "bf16x3 (fp32 operands split hi+lo, 3 tcgen05 products, fp32 accumulate)" if enc16 == 0 else
+                          "fp16 (1 tcgen05 product, fp32 accumulate) in encoder stages 1-%d; bf16x3 (operands split hi+lo, 3 products) "
+                          "in the other stages, the U-nets and the decoders" % enc16),
                 "data": "synthetic",
                 "config": {"workload": workload,
-                           "seq_len": L, "strands": 2, "models": 1, "kernels": args.kernels,
+                           "seq_len": L, "strands": 2, "models": 1, "kernels": args.kernels, "encoder_fp16_stages": enc16,
                            "l2": "inputs (512 MB) and stage activations (>1 GB per chunk) exceed the 126 MB L2",
                            "parallelism": "sequence-sharded encoder x%d + all-gather, strand-parallel cascades" % world
                            if world > 1 else "single GPU"},
@@ -315,8 +337,8 @@ def main():
             full = 2 * (320 * tb + 8 * te / 3 + 4 * td) if big else cpu_extrapolate(tb, te, td, tm)
             line["cpu_baseline"] = {
                 "value": 2 * L / full / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
-                "sample": "1 of 40 encoder blocks (912 kb incl. halo), Encoder2@8000, 1 Decoder, 1 Decoder_1m; "
-                          "extrapolated to the full 2-strand step", "sample_wall_s": time.perf_counter() - t0,
+                "sample": CPU_SAMPLE + "; extrapolated linearly to the full 2-strand step",
+                "sample_wall_s": time.perf_counter() - t0,
                 "maps_per_s": maps_per_step / full}
         print(json.dumps(line))
     if world > 1:

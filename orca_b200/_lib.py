@@ -40,6 +40,7 @@ SIGNATURES = {
     "orca_b200_get_impl": (ctypes.c_int, []),
     "orca_b200_launch_count": (ctypes.c_uint64, []),
     "orca_b200_set_decoder_program": (ctypes.c_int, [ctypes.c_int]),
+    "orca_b200_set_encoder_fp16_stages": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_profile_summary": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64]),
     "orca_b200_module_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ConvParams), ctypes.c_int32,
@@ -96,6 +97,11 @@ def check(status):
 
 def set_impl(impl):
     check(lib().orca_b200_set_impl({"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC}.get(impl, impl)))
+
+
+def set_encoder_fp16_stages(n):
+    """Leading encoder stages in single-pass fp16 (0..7, -1 = default 3); returns the previous setting."""
+    return int(lib().orca_b200_set_encoder_fp16_stages(int(n)))
 
 
 def launch_count():

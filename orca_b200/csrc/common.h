@@ -50,6 +50,7 @@ struct ConvLayer {
   // tensor-core images (bf16 hi/lo split, UMMA-swizzled), optional
   void* tc_w = nullptr;
   size_t tc_w_bytes = 0;
+  void* tc_w16 = nullptr;  // Conv1d k=9 only: fp16 image for the single-pass encoder stages (conv_tc.cu, FMT = 1)
   // extra input channels of the Decoder combiners (the 129th / 65th channel in orca_modules, num_2d of them in
   // orca_leukemia), kept out of the aligned implicit GEMM: w_extra[n_extra][tap][c_out]
   float* w_extra = nullptr;

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const size_t off = (((size_t)b * 8 + (c0 >> 3) + ch) * npad + row + 4) * 8;
-        split_store8(v + 8 * ch, out_hi + off, out_lo + off);
+        if (out_lo) split_store8(v + 8 * ch, out_hi + off, out_lo + off);  // bf16 hi/lo planes
+        else store_h8(v + 8 * ch, out_hi + off);                           // one fp16 plane (single-pass stages)
       }
     }
   }
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
       const int p = i / per_plane, j = i - p * per_plane;
       const size_t r = ((size_t)b * 8 + p) * npad + (j < 4 ? j : tail0 + (j - 4));
       reinterpret_cast<uint4*>(out_hi)[r] = make_uint4(0, 0, 0, 0);
-      reinterpret_cast<uint4*>(out_lo)[r] = make_uint4(0, 0, 0, 0);
+      if (out_lo) reinterpret_cast<uint4*>(out_lo)[r] = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -165,10 +166,14 @@ __global__ void __launch_bounds__(64) lconv1_edge_kernel(const SeqIn in, long lo
       const int pi = (int)(p - p0);
       for (int m = 0; m < 64; ++m) acc = fmaf(y1[pi][m], w2[(t * 64 + m) * 64 + co], acc);
     }
-    const __nv_bfloat16 h = __float2bfloat16_rn(acc);
     const size_t off = (((size_t)b * 8 + (co >> 3)) * npad + (size_t)(l - l_begin) + 4) * 8 + (co & 7);
-    out_hi[off] = h;
-    out_lo[off] = __float2bfloat16_rn(acc - __bfloat162float(h));
+    if (out_lo) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+      out_hi[off] = h;
+      out_lo[off] = __float2bfloat16_rn(acc - __bfloat162float(h));
+    } else {
+      reinterpret_cast<__half*>(out_hi)[off] = __float2half_rn(acc);
+    }
   }
 }
 
@@ -251,11 +256,13 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb,
     configured = true;
   }
   lconv1_tc_kernel<<<grid, 128, kSmem, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
-                                        L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
+                                        L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi),
+                                        out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo));
   ORCA_LAUNCH_OK();
   if (l_begin == 0 || l_begin + n == Ltot) {
     lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,
-                                                            static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
+                                                            static_cast<__nv_bfloat16*>(out->hi),
+                                                            out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo));
     ORCA_LAUNCH_OK();
   }
   return ORCA_B200_OK;

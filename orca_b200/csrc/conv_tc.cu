@@ -23,6 +23,7 @@
 // plus compile-time offsets (loops over taps / K steps are fully unrolled).  mbarrier rings: A slots (one
 // 64-channel K-block of one tile), weight stages (one (K-block, tap) image), 2 TMEM accumulators.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -38,8 +39,7 @@ namespace {
 using namespace tcdev;
 
 constexpr int kRows = 136;                       // 128 output rows + 8 halo rows per A slot
-constexpr int kASlotBytes = 2 * 8 * kRows * 16;  // hi + lo images of a 64-channel K-block
-constexpr int kALoOff = 8 * kRows * 16;
+constexpr int kALoOff = 8 * kRows * 16;          // FMT 0: the lo image of a 64-channel K-block follows the hi image
 constexpr int kEpiWarps = 8;                    // two per TMEM lane quarter, each takes every other 32-column group
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 producer, warp 1 MMA issuer, then the epilogue warps
 
@@ -55,17 +55,23 @@ struct TcKArgs {
   int tiles_per_sample, total_tiles;
 };
 
-template <int C_IN, int C_OUT>
+// FMT 0: operands are bf16 hi/lo pairs, three products per conv (fp32-grade accuracy).
+// FMT 1: operands are single fp16 images, ONE product per conv: a third of the tensor-core work and half the
+//        activation bytes.  Used for the early encoder stages, whose rounding noise (2^-12 per element,
+//        incoherent) is averaged away by the pooling + 1152-term sums of the later stages.
+template <int C_IN, int C_OUT, int FMT>
 struct TcCfg {
   static constexpr int NKB = (C_IN + 63) / 64;
-  static constexpr int STAGE_MAX = 2 * 8 * C_OUT * 16;  // [Bh;Bl] of a 64-channel K-block
-  static constexpr int NW = C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3);
-  static constexpr int NA = C_OUT == 64 ? 2 : 3;
+  static constexpr int PARTS = FMT ? 1 : 2;               // operand images per K chunk
+  static constexpr int A_SLOT = PARTS * 8 * kRows * 16;   // one 64-channel K-block of a tile
+  static constexpr int STAGE_MAX = PARTS * 8 * C_OUT * 16;  // weights of one (64-channel K-block, tap)
+  static constexpr int NW = FMT ? (C_OUT == 128 ? 6 : 9) : (C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3));
+  static constexpr int NA = FMT ? 4 : (C_OUT == 64 ? 2 : 3);
   static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
-  static constexpr int SMEM = NA * kASlotBytes + NW * STAGE_MAX + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
+  static constexpr int SMEM = NA * A_SLOT + NW * STAGE_MAX + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
   __host__ __device__ static constexpr int kb_size(int kb) { return (kb == NKB - 1) ? C_IN - 64 * (NKB - 1) : 64; }
-  __host__ __device__ static constexpr int stage_bytes(int kb) { return 2 * (kb_size(kb) / 8) * C_OUT * 16; }
+  __host__ __device__ static constexpr int stage_bytes(int kb) { return PARTS * (kb_size(kb) / 8) * C_OUT * 16; }
   __host__ __device__ static constexpr int stage_offset(int kb, int tap) {
     int off = 0;
     for (int i = 0; i < kb; ++i) off += 9 * stage_bytes(i);
@@ -75,12 +81,14 @@ struct TcCfg {
 
 // CONCAT: the two products that share A = Ah run as ONE MMA against B = [Bh;Bl] (N = 2*C_OUT, two
 // accumulator column blocks summed in the epilogue) -- 2 MMAs and 2 A-operand reads per K step instead of 3.
-template <int C_IN, int C_OUT, bool CONCAT>
+template <int C_IN, int C_OUT, bool CONCAT, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a) {
-  using Cfg = TcCfg<C_IN, C_OUT>;
+  using Cfg = TcCfg<C_IN, C_OUT, FMT>;
+  static_assert(!(FMT && CONCAT), "the single-pass format has nothing to concatenate");
   constexpr int NKB = Cfg::NKB, NW = Cfg::NW, NA = Cfg::NA;
+  constexpr int kASlotBytes = Cfg::A_SLOT;
   constexpr bool RESIDENT = Cfg::RESIDENT;
-  constexpr uint32_t ACC_STRIDE = CONCAT ? Cfg::ACC_STRIDE_CAT : 128;
+  constexpr uint32_t ACC_STRIDE = FMT ? (C_OUT == 64 ? 64 : 128) : (CONCAT ? Cfg::ACC_STRIDE_CAT : 128);
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
@@ -123,14 +131,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
         const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
         mbar_wait(bA_empty + 8 * slot, ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(bA_full + 8 * slot, 2u * kc * kRows * 16);
+          mbar_expect_tx(bA_full + 8 * slot, (uint32_t)Cfg::PARTS * kc * kRows * 16);
           const uint32_t dst = smem_u32(sA) + slot * kASlotBytes;
           const size_t plane0 = (size_t)b * (C_IN / 8) + kb * 8;
 #pragma unroll
           for (int c = 0; c < kc; ++c) {
             const size_t off = ((plane0 + c) * a.npad_in + row0) * 8;
             bulk_g2s(dst + c * kRows * 16, a.in_hi + off, kRows * 16, bA_full + 8 * slot);
-            bulk_g2s(dst + kALoOff + c * kRows * 16, a.in_lo + off, kRows * 16, bA_full + 8 * slot);
+            if (!FMT) bulk_g2s(dst + kALoOff + c * kRows * 16, a.in_lo + off, kRows * 16, bA_full + 8 * slot);
           }
         }
         __syncwarp();
@@ -152,8 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
     }
   } else if (warp == 1) {
     // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
-    constexpr uint32_t idesc = umma_idesc_bf16(C_OUT), idesc_cat = umma_idesc_bf16(2 * C_OUT);
-    constexpr uint32_t bLbo = 2 * C_OUT * 16;  // chunk image = [Bh rows][Bl rows]
+    constexpr uint32_t idesc = FMT ? umma_idesc_f16(C_OUT) : umma_idesc_bf16(C_OUT), idesc_cat = umma_idesc_bf16(2 * C_OUT);
+    constexpr uint32_t bLbo = Cfg::PARTS * C_OUT * 16;  // chunk image = [Bh rows][Bl rows] (FMT 0) or [B rows] (FMT 1)
     uint32_t a_it = 0, w_it = 0, acc_it = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
@@ -181,7 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
                 const uint64_t ah = umma_desc64(ao), al = umma_desc64(ao + (kALoOff >> 4));
                 const uint64_t bh = umma_desc64(bLo + ks * ((2 * bLbo) >> 4));
                 const uint32_t accum = (kb | tap | ks) != 0 ? 1u : 0u;
-                if (CONCAT) {
+                if (FMT) {
+                  umma_bf16(d_tmem, ah, bh, idesc, accum);      // fp16 A * fp16 B, the only product
+                } else if (CONCAT) {
                   umma_bf16(d_tmem, ah, bh, idesc_cat, accum);  // [Ah*Bh | Ah*Bl]
                   umma_bf16(d_tmem, al, bh, idesc, 1u);         // += Al*Bh into the first block
                 } else {
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
         const int p = i / per_plane, j = i - p * per_plane;
         const size_t r = (size_t)p * a.npad_out + (j < 4 ? j : tail0 + (j - 4));
         reinterpret_cast<uint4*>(a.out_hi)[r] = make_uint4(0, 0, 0, 0);
-        reinterpret_cast<uint4*>(a.out_lo)[r] = make_uint4(0, 0, 0, 0);
+        if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo)[r] = make_uint4(0, 0, 0, 0);
       }
     }
     uint32_t acc_it = 0;
@@ -238,8 +248,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_in + r_in) * 8;
-            add_hilo8(dst + 8 * ch, a.res_hi + off, a.res_lo + off);
-            if (a.res2_hi) add_hilo8(dst + 8 * ch, a.res2_hi + off, a.res2_lo + off);
+            if (FMT) {  // residuals share the input's format
+              add_h8(dst + 8 * ch, a.res_hi + off);
+              if (a.res2_hi) add_h8(dst + 8 * ch, a.res2_hi + off);
+            } else {
+              add_hilo8(dst + 8 * ch, a.res_hi + off, a.res_lo + off);
+              if (a.res2_hi) add_hilo8(dst + 8 * ch, a.res2_hi + off, a.res2_lo + off);
+            }
           }
         }
       };
@@ -291,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_out + lo_row + 4) * 8;
-              split_store8(v + 8 * ch, a.out_hi + off, a.out_lo + off);
+              if (a.out_lo) split_store8(v + 8 * ch, a.out_hi + off, a.out_lo + off);  // bf16 hi/lo planes
+              else store_h8(v + 8 * ch, a.out_hi + off);                               // one fp16 plane
             }
           }
         }
@@ -306,19 +322,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
-template <int C_IN, int C_OUT, bool CONCAT>
+template <int C_IN, int C_OUT, bool CONCAT, int FMT>
 int launch_tc_impl(const TcKArgs& a, int sms, cudaStream_t s) {
-  using Cfg = TcCfg<C_IN, C_OUT>;
+  using Cfg = TcCfg<C_IN, C_OUT, FMT>;
   static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& configured = configured_dev[cur_dev & 31];
   if (!configured) {
-    ORCA_CUDA_OK(cudaFuncSetAttribute(conv1d_tc_kernel<C_IN, C_OUT, CONCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    ORCA_CUDA_OK(cudaFuncSetAttribute(conv1d_tc_kernel<C_IN, C_OUT, CONCAT, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv1d_tc_kernel<C_IN, C_OUT, CONCAT><<<grid, kThreads, Cfg::SMEM, s>>>(a);
+  conv1d_tc_kernel<C_IN, C_OUT, CONCAT, FMT><<<grid, kThreads, Cfg::SMEM, s>>>(a);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }
@@ -334,10 +350,11 @@ int concat_mask() {
 }
 
 template <int C_IN, int C_OUT>
-int launch_tc(const TcKArgs& a, int sms, cudaStream_t s) {
+int launch_tc(const TcKArgs& a, int sms, cudaStream_t s, int fmt) {
+  if (fmt) return launch_tc_impl<C_IN, C_OUT, false, 1>(a, sms, s);
   const int bit = C_OUT == 64 ? 1 : (C_OUT == 96 ? 2 : 4);
-  if (concat_mask() & bit) return launch_tc_impl<C_IN, C_OUT, true>(a, sms, s);
-  return launch_tc_impl<C_IN, C_OUT, false>(a, sms, s);
+  if (concat_mask() & bit) return launch_tc_impl<C_IN, C_OUT, true, 0>(a, sms, s);
+  return launch_tc_impl<C_IN, C_OUT, false, 0>(a, sms, s);
 }
 
 // ---- first layer (4 -> 64) writing chunk planes; pool-5 on planes ---------------------------------
@@ -418,6 +435,8 @@ __global__ void __launch_bounds__(256) conv_first_planes_kernel(const SeqIn in, 
 __global__ void pool_planes_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int planes,
                                    int n_out, int npad_in, int npad_out, int p) {
+  // in_lo == NULL: the input is one fp16 plane; out_lo == NULL: write one fp16 plane (this kernel is also where the
+  // single-pass encoder stages hand over to the bf16 hi/lo stages)
   const int per_plane = npad_out;  // also writes the zero pad rows
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)planes * per_plane;
        i += (long long)gridDim.x * blockDim.x) {
@@ -426,7 +445,7 @@ __global__ void pool_planes_kernel(const __nv_bfloat16* __restrict__ in_hi, cons
     float m[8];
     if (lo_row < 0 || lo_row >= n_out) {
       reinterpret_cast<uint4*>(out_hi)[i] = make_uint4(0, 0, 0, 0);
-      reinterpret_cast<uint4*>(out_lo)[i] = make_uint4(0, 0, 0, 0);
+      if (out_lo) reinterpret_cast<uint4*>(out_lo)[i] = make_uint4(0, 0, 0, 0);
       continue;
     }
 #pragma unroll
@@ -434,11 +453,13 @@ __global__ void pool_planes_kernel(const __nv_bfloat16* __restrict__ in_hi, cons
     for (int k = 0; k < p; ++k) {
       float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const size_t off = ((size_t)pl * npad_in + (size_t)lo_row * p + k + 4) * 8;
-      add_hilo8(v, in_hi + off, in_lo + off);
+      if (in_lo) add_hilo8(v, in_hi + off, in_lo + off);
+      else add_h8(v, in_hi + off);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
     }
-    split_store8(m, out_hi + (size_t)i * 8, out_lo + (size_t)i * 8);
+    if (out_lo) split_store8(m, out_hi + (size_t)i * 8, out_lo + (size_t)i * 8);
+    else store_h8(m, out_hi + (size_t)i * 8);
   }
 }
 
@@ -492,6 +513,26 @@ int tc_pack_layer(ConvLayer& L, const float* w /*[tap][c_in][c_out]*/, std::vect
   ORCA_CUDA_OK(cudaMemcpy(d, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   L.tc_w = d;
   L.tc_w_bytes = img.size() * 2;
+  // fp16 image for the single-pass format: same stage order, [k-chunk][c_out rows][8] fp16 per (K-block, tap)
+  std::vector<uint16_t> img16;
+  img16.reserve((size_t)9 * L.c_in * L.c_out);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int ks = (kb == nkb - 1) ? L.c_in - 64 * (nkb - 1) : 64;
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c = 0; c < ks / 8; ++c)
+        for (int n = 0; n < L.c_out; ++n)
+          for (int j = 0; j < 8; ++j) {
+            const __half hv = __float2half_rn(w[((size_t)tap * L.c_in + kb * 64 + c * 8 + j) * L.c_out + n]);
+            uint16_t bits;
+            memcpy(&bits, &hv, 2);
+            img16.push_back(bits);
+          }
+  }
+  void* d16 = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&d16, img16.size() * 2));
+  allocs.push_back(d16);
+  ORCA_CUDA_OK(cudaMemcpy(d16, img16.data(), img16.size() * 2, cudaMemcpyHostToDevice));
+  L.tc_w16 = d16;
   return ORCA_B200_OK;
 }
 
@@ -514,20 +555,22 @@ static int sm_count() {
 
 int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32, int pool,
               int relu, cudaStream_t s, const TcAct* res2) {
-  if (!L.tc_w) { set_error("tc_conv1d: layer %d->%d has no tensor-core weights", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
+  const int fmt = in.fmt;
+  if (!(fmt ? L.tc_w16 : L.tc_w)) { set_error("tc_conv1d: layer %d->%d has no tensor-core weights", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED; }
+  if ((res && res->fmt != fmt) || (res2 && res2->fmt != fmt)) { set_error("tc_conv1d: residual format differs from the input format"); return ORCA_B200_EINVAL; }
   if (in.C != L.c_in || (pool != 1 && pool != 2 && pool != 4) || in.n % pool != 0 || (out_planes == nullptr && out_f32 == nullptr) || (res2 && !res)) {
     set_error("tc_conv1d: bad call (C=%d c_in=%d pool=%d n=%lld)", in.C, L.c_in, pool, (long long)in.n);
     return ORCA_B200_EINVAL;
   }
   TcKArgs a;
   a.in_hi = static_cast<const __nv_bfloat16*>(in.hi); a.in_lo = static_cast<const __nv_bfloat16*>(in.lo);
-  a.w = static_cast<const uint8_t*>(L.tc_w); a.bias = L.b;
+  a.w = static_cast<const uint8_t*>(fmt ? L.tc_w16 : L.tc_w); a.bias = L.b;
   a.res_hi = res ? static_cast<const __nv_bfloat16*>(res->hi) : nullptr;
   a.res_lo = res ? static_cast<const __nv_bfloat16*>(res->lo) : nullptr;
   a.res2_hi = res2 ? static_cast<const __nv_bfloat16*>(res2->hi) : nullptr;
   a.res2_lo = res2 ? static_cast<const __nv_bfloat16*>(res2->lo) : nullptr;
   a.out_hi = out_planes ? static_cast<__nv_bfloat16*>(out_planes->hi) : nullptr;
-  a.out_lo = out_planes ? static_cast<__nv_bfloat16*>(out_planes->lo) : nullptr;
+  a.out_lo = (out_planes && out_planes->fmt == 0) ? static_cast<__nv_bfloat16*>(out_planes->lo) : nullptr;  // NULL: one fp16 plane
   a.out_f32 = out_f32;
   a.nb = in.nb; a.n = (int)in.n; a.npad_in = (int)in.npad; a.n_out = (int)(in.n / pool);
   a.npad_out = out_planes ? (int)out_planes->npad : 0;
@@ -540,18 +583,18 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
   const int sms = sm_count();
   const int key = L.c_in * 1000 + L.c_out;
   switch (key) {
-    case 64064: return launch_tc<64, 64>(a, sms, s);
-    case 64096: return launch_tc<64, 96>(a, sms, s);
-    case 96096: return launch_tc<96, 96>(a, sms, s);
-    case 96128: return launch_tc<96, 128>(a, sms, s);
-    case 128128: return launch_tc<128, 128>(a, sms, s);
+    case 64064: return launch_tc<64, 64>(a, sms, s, fmt);
+    case 64096: return launch_tc<64, 96>(a, sms, s, fmt);
+    case 96096: return launch_tc<96, 96>(a, sms, s, fmt);
+    case 96128: return launch_tc<96, 128>(a, sms, s, fmt);
+    case 128128: return launch_tc<128, 128>(a, sms, s, fmt);
     default: set_error("tc_conv1d: no kernel for %d->%d", L.c_in, L.c_out); return ORCA_B200_EUNSUPPORTED;
   }
 }
 
 int tc_conv_first(const ConvLayer& L, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n, TcAct* out,
                   cudaStream_t s) {
-  if (L.c_in != 4 || L.c_out != 64 || out->C != 64 || out->n != n || out->nb != nb) { set_error("tc_conv_first: bad geometry"); return ORCA_B200_EINVAL; }
+  if (L.c_in != 4 || L.c_out != 64 || out->C != 64 || out->n != n || out->nb != nb || out->fmt != 0) { set_error("tc_conv_first: bad geometry"); return ORCA_B200_EINVAL; }
   dim3 grid((unsigned)((n + 127) / 128), (unsigned)nb), block(256);
   conv_first_planes_kernel<<<grid, block, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L.w, L.b,
                                                   static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo));
@@ -565,8 +608,8 @@ int tc_pool_planes(const TcAct& in, TcAct* out, int p, cudaStream_t s) {
   const long long total = (long long)planes * out->npad;
   unsigned grid = (unsigned)((total + 255) / 256);
   if (grid > 148u * 16u) grid = 148u * 16u;
-  pool_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in.hi), static_cast<const __nv_bfloat16*>(in.lo),
-                                          static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), planes,
+  pool_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in.hi), in.fmt ? nullptr : static_cast<const __nv_bfloat16*>(in.lo),
+                                          static_cast<__nv_bfloat16*>(out->hi), out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo), planes,
                                           (int)out->n, (int)in.npad, (int)out->npad, p);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;

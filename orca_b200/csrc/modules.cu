@@ -218,12 +218,25 @@ static int encoder_window(const ConvLayer* L, const SeqIn& x, int nb, int64_t Lt
 
 // Same program on the tcgen05 path: activations are bf16 hi/lo chunk planes (tc.h); bias/ReLU/residual
 // and the 4x / 2x max-pools are fused into the conv epilogue, the three 5x pools run as a plane kernel.
-static TcAct tc_make(void* base, int nb, int C, int64_t n) {
+static TcAct tc_make(void* base, int nb, int C, int64_t n, int fmt = 0) {
   TcAct t;
-  t.nb = nb; t.C = C; t.n = n; t.npad = tc_npad(n);
+  t.nb = nb; t.C = C; t.n = n; t.npad = tc_npad(n); t.fmt = fmt;
   t.hi = base;
-  t.lo = base ? static_cast<char*>(base) + tc_plane_bytes(nb, C, n) : nullptr;
+  t.lo = (base && !fmt) ? static_cast<char*>(base) + tc_plane_bytes(nb, C, n) : nullptr;
   return t;
+}
+
+// Number of leading encoder stages that run in the single-pass fp16 format (conv_tc.cu, FMT = 1); the rest, the
+// U-nets and the decoders keep the three-product bf16 hi/lo format.  -1 = default (env ORCA_B200_ENC_FP16_STAGES,
+// else 3: stages 1-3 are 97 % of the encoder FLOP and their rounding noise does not survive stages 4-7).
+static std::atomic<int> g_enc_fp16_stages{-1};
+static int encoder_fp16_stages() {
+  int v = g_enc_fp16_stages.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("ORCA_B200_ENC_FP16_STAGES");
+    v = e ? atoi(e) : 3;
+  }
+  return v < 0 ? 0 : (v > 7 ? 7 : v);
 }
 
 static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32,
@@ -235,7 +248,7 @@ static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res,
   ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
   const int st = tc_conv1d(L, in, res, out_planes, out_f32, pool, relu, s, res2);
   ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
-  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = 0; r.tc = 1;  // dil = 0 marks Conv1d in the profile
+  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = 0; r.tc = in.fmt ? 2 : 1;  // dil = 0 marks Conv1d; tc = 2: single-pass fp16
   r.flop = 2.0 * (double)in.nb * (double)in.n * L.c_in * L.c_out * 9;
   g_prof.push_back(r);
   return st;
@@ -252,10 +265,15 @@ static int encoder_window_tc(const ConvLayer* L, const SeqIn& x, int nb, int64_t
   if (!ar.dry) {
     int64_t len = n;
     TcAct in;  // input of the stage (pooled output of the previous one)
+    // the first n16 stages run single-pass fp16 (needs the composed lconv1 and fp16 weight images everywhere)
+    int n16 = L[0].tc_w ? encoder_fp16_stages() : 0;
+    for (int i = 1; i < 4 * n16; ++i)
+      if (!L[i].tc_w16) n16 = 0;
     for (int k = 0; k < 7; ++k) {
       const ConvLayer* Lk = L + 4 * k;
       const int C = Lk[0].c_out;
-      TcAct t0 = tc_make(X[0], nb, C, len), t1 = tc_make(X[1], nb, C, len), t2 = tc_make(X[2], nb, C, len);
+      const int f = k < n16 ? 1 : 0, fnext = k + 1 < n16 ? 1 : 0;  // format of this stage / of the next stage's input
+      TcAct t0 = tc_make(X[0], nb, C, len, f), t1 = tc_make(X[1], nb, C, len, f), t2 = tc_make(X[2], nb, C, len, f);
       if (k == 0 && Lk[0].tc_w) {
         // lconv1 (two linear convs) as ONE composed k=17 tensor-core conv straight from the input (conv_first_tc.cu)
         ORCA_TRY(tc_lconv1(Lk[0], Lk[1], x, nb, Ltot, l_begin, n, &t1, s));
@@ -273,7 +291,7 @@ static int encoder_window_tc(const ConvLayer* L, const SeqIn& x, int nb, int64_t
         break;
       }
       const int p = kPool[k + 1];
-      TcAct nxt = tc_make(Pb, nb, C, len / p);
+      TcAct nxt = tc_make(Pb, nb, C, len / p, fnext);
       if (p == 5) {
         ORCA_TRY(tc_conv1d(Lk[3], t0, &t1, &t2, nullptr, 1, 1, s));  // out_k + lout_k
         ORCA_TRY(tc_pool_planes(t2, &nxt, 5, s));
@@ -865,6 +883,11 @@ int orca_b200_get_impl(void) { return g_impl.load(); }
 int orca_b200_set_decoder_program(int on) {
   const int prev = g_dec_program.load();
   g_dec_program.store(on < 0 ? -1 : (on ? 1 : 0));
+  return prev;
+}
+int orca_b200_set_encoder_fp16_stages(int n) {
+  const int prev = encoder_fp16_stages();
+  g_enc_fp16_stages.store(n < 0 ? -1 : (n > 7 ? 7 : n));
   return prev;
 }
 int orca_b200_set_impl(int impl) {

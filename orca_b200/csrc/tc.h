@@ -8,11 +8,14 @@ namespace orca {
 
 // ---- 1D: (nb, C, n) activation as two bf16 planes hi/lo[nb][C/8][npad][8]; data row l lives at row
 // l + 4, rows [0,4) and [n+4, npad) are zero (they are the convolution's zero padding).
+// fmt 0: two bf16 planes (x = hi + lo, three tensor-core products per conv); fmt 1: ONE fp16 plane in `hi`
+// (lo unused; one tensor-core product per conv) -- the early encoder stages, see modules.cu encoder_window_tc.
 struct TcAct {
   void* hi = nullptr;
   void* lo = nullptr;
   int nb = 0, C = 0;
   int64_t n = 0, npad = 0;
+  int fmt = 0;
 };
 
 inline int64_t tc_npad(int64_t n) { return ((n + 127) / 128) * 128 + 8; }

@@ -2,6 +2,7 @@
 // tcgen05.mma / commit / ld, and bf16 hi/lo split helpers.  (Inline PTX; no CUTLASS dependency.)
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace orca {
@@ -37,6 +38,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N=n
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// same with A=B=fp16 (format code 0): the single-pass encoder stages (see conv_tc.cu, FMT = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -86,6 +91,26 @@ __device__ __forceinline__ void split_store8(const float* v, __nv_bfloat16* hi_d
   for (int j = 0; j < 4; ++j) split_pack2(v[2 * j], v[2 * j + 1], h[j], l[j]);
   *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// fp16 single-plane variants: 8 fp32 -> 8 fp16 (round to nearest), one 16-byte store; v[0..8) += 8 fp16
+__device__ __forceinline__ void store_h8(const float* v, void* dst) {
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+}
+__device__ __forceinline__ void add_h8(float* v, const void* src) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+  }
 }
 // v[0..8) += hi + lo
 __device__ __forceinline__ void add_hilo8(float* v, const __nv_bfloat16* hi_src, const __nv_bfloat16* lo_src) {

@@ -60,6 +60,16 @@ def test_encoder_golden(name, impl):
     e = relerr(y.cpu().numpy(), g["out"])
     print(name, impl, "relerr %.2e" % e)
     assert e <= tol(impl)
+    if impl == "auto":  # encoder precision settings: three-product bf16 everywhere (0), default (3), single-pass fp16 everywhere (7)
+        errs = {}
+        for stages in (0, 3, 7):
+            _lib.set_encoder_fp16_stages(stages)
+            try:
+                errs[stages] = relerr(m(x).cpu().numpy(), g["out"])
+            finally:
+                _lib.set_encoder_fp16_stages(-1)
+        print(name, "relerr by fp16 stages", {k: "%.2e" % v for k, v in errs.items()})
+        assert errs[0] <= 5e-5 and errs[3] <= 1e-4 and errs[7] <= TOL
 
 
 def test_encoder_layouts_and_chunks(impl):
