@@ -12,6 +12,7 @@
 // dilation, exactly like conv2d_tc_kernel) and re-initialises the A/W ring barriers; the two TMEM accumulator
 // barriers run across layers.  The per-layer math (row-run A operands, [Bh;Bl] concat MMAs, epilogue) is the
 // single-layer kernel's (conv2d_tc.cu).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -41,6 +42,8 @@ struct Tc2dLayer {
 struct Tc2dGeom {
   long long plane_rows;
   int nb, S, Wp, tiles_per_row, total_tiles, n_layers, oper_bytes;
+  int experiment;  // diagnostic (env ORCA_B200_DEC_EXPERIMENT; results are WRONG when non-zero): bit 0 epilogue without
+                   // global loads/stores, bit 1 producer copies 16 B per run chunk, bit 2 no MMAs, bit 3 no TMEM loads
 };
 
 struct Bars {
@@ -82,6 +85,7 @@ __device__ __forceinline__ void producer_layer(const Tc2dLayer& L, const Tc2dGeo
   const int nkb = (L.c_in + 63) / 64, R = 128 + 2 * L.d, kc = (L.c_in < 64 ? L.c_in : 64) / 8;
   const uint32_t aLoOff = (uint32_t)kc * R * 16, tapBytes = 2u * kc * L.c_out * 16;
   uint32_t a_it = 0, w_it = 0, loaded = (preloaded && L.resident) ? 0xFFFFFFFFu : 0u;
+  const int lane = threadIdx.x & 31;
   for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
     int b, y, x0;
     tile_coords(g, tile, b, y, x0);
@@ -99,19 +103,25 @@ __device__ __forceinline__ void producer_layer(const Tc2dLayer& L, const Tc2dGeo
         const bool need_w = L.resident ? !((loaded >> sid) & 1u) : true;
         const uint32_t ws = L.resident ? (uint32_t)sid : w_it % L.NW;
         if (!L.resident) mbar_wait(B.w_empty + 8 * ws, ((w_it / L.NW) & 1) ^ 1);
+        // One bulk copy per (8-channel chunk, hi|lo) = up to 16 per run.  Issued by one lane they cost ~65 cycles
+        // each back to back and the producer warp paced the whole layer (tools/decoder_phases.py: 1.65 us per tile
+        // with every other role switched off); issued by 16 lanes of the warp at once they overlap.  A 3-D TMA tensor
+        // copy (box {16 B, R, kc}) was measured SLOWER than either: its 16-byte inner extent starves the TMA engine.
+        const uint32_t run_bytes = (g.experiment & 2) ? 16u : (uint32_t)R * 16;
         if (elect_one()) {
-          mbar_expect_tx(B.a_full + 8 * slot, 2u * kc * R * 16);
-          const uint32_t dst = sA + slot * L.a_slot_bytes;
-          for (int c = 0; c < kc; ++c) {
-            const long long plane = (long long)b * (L.c_in / 8) + kb * 8 + c;
-            const long long off = (plane * g.plane_rows + row0) * 8;
-            bulk_g2s(dst + c * R * 16, L.in_hi + off, R * 16, B.a_full + 8 * slot);
-            bulk_g2s(dst + aLoOff + c * R * 16, L.in_lo + off, R * 16, B.a_full + 8 * slot);
-          }
+          mbar_expect_tx(B.a_full + 8 * slot, 2u * kc * run_bytes);
           if (need_w) {
             mbar_expect_tx(B.w_full + 8 * ws, 3 * tapBytes);
             bulk_g2s(sW + ws * L.w_stage_bytes, L.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, B.w_full + 8 * ws);
           }
+        }
+        __syncwarp();
+        if (lane < 2 * kc) {
+          const int c = lane >> 1, part = lane & 1;
+          const uint32_t dst = sA + slot * L.a_slot_bytes + (part ? aLoOff : 0u) + c * R * 16;
+          const long long plane = (long long)b * (L.c_in / 8) + kb * 8 + c;
+          const long long off = (plane * g.plane_rows + row0) * 8;
+          bulk_g2s(dst, (part ? L.in_lo : L.in_hi) + off, run_bytes, B.a_full + 8 * slot);
         }
         __syncwarp();
         ++a_it;
@@ -163,7 +173,8 @@ __device__ __forceinline__ void mma_layer(const Tc2dLayer& L, const Tc2dGeom& g,
         const uint32_t aLo = __shfl_sync(0xffffffffu, umma_desc_lo(sA + slot * L.a_slot_bytes, R * 16), 0);
         const uint32_t bLo = __shfl_sync(0xffffffffu, umma_desc_lo(sW + ws * L.w_stage_bytes, 2 * C_OUT * 16), 0);
         if (elect_one()) {
-          if (si == 0) issue_stage<C_OUT, KSTEPS, true>(d_tmem, aLo, bLo, aStep, aLoStep, tapStep, (uint32_t)L.d, kb == 0);
+          if (g.experiment & 4) {}
+          else if (si == 0) issue_stage<C_OUT, KSTEPS, true>(d_tmem, aLo, bLo, aStep, aLoStep, tapStep, (uint32_t)L.d, kb == 0);
           else issue_stage<C_OUT, KSTEPS, false>(d_tmem, aLo, bLo, aStep, aLoStep, tapStep, (uint32_t)L.d, false);
           if (!L.resident) umma_commit(B.w_empty + 8 * ws);
           umma_commit(B.a_empty + 8 * slot);
@@ -189,7 +200,7 @@ __device__ __forceinline__ void epilogue_layer(const Tc2dLayer& L, const Tc2dGeo
     tile_coords(g, tile, b, y, x0);
     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
     const int x = x0 + q * 32 + lane;
-    const bool valid = x < g.S;
+    const bool valid = x < g.S && !(g.experiment & 1);
     const long long r = (long long)y * g.Wp + kPX + x;
     float res[MYU][16];
 #pragma unroll
@@ -218,8 +229,10 @@ __device__ __forceinline__ void epilogue_layer(const Tc2dLayer& L, const Tc2dGeo
     for (int u = 0; u < MYU; ++u) {
       const int c0 = 16 * (h + 2 * u);
       uint32_t raw[16], raw2[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + C_OUT + c0, raw2);
+      if (!(g.experiment & 8)) {
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + c0, raw);
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + as * 128 + C_OUT + c0, raw2);
+      }
       if (valid) {
         float v[16];
 #pragma unroll
@@ -389,10 +402,14 @@ size_t Tc2dProgram::scratch_bytes(int max_layers) { return (size_t)max_layers * 
 int Tc2dProgram::run(void* scratch, size_t scratch_bytes_, cudaStream_t s) {
   const int n = (int)impl->layers.size();
   if (n == 0) return ORCA_B200_OK;
-  if (scratch_bytes_ < (size_t)n * sizeof(Tc2dLayer) + 256) { set_error("Tc2dProgram: scratch too small"); return ORCA_B200_EWORKSPACE; }
+  if (scratch_bytes_ < scratch_bytes(n)) { set_error("Tc2dProgram: scratch too small"); return ORCA_B200_EWORKSPACE; }
   Tc2dGeom g = impl->g;
   g.n_layers = n;
   g.oper_bytes = (impl->oper_bytes + 127) & ~127;
+  {
+    const char* e = getenv("ORCA_B200_DEC_EXPERIMENT");
+    g.experiment = e ? atoi(e) : 0;
+  }
   unsigned int* counter = static_cast<unsigned int*>(scratch);
   Tc2dLayer* d_layers = reinterpret_cast<Tc2dLayer*>(static_cast<char*>(scratch) + 256);
   ORCA_CUDA_OK(cudaMemsetAsync(counter, 0, 256, s));

@@ -121,17 +121,18 @@ __global__ void __launch_bounds__(kThreads2d, 1) conv2d_tc_kernel(const Tc2dKArg
           if (!a.resident) mbar_wait(bW_empty + 8 * ws, ((w_it / NW) & 1) ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bA_full + 8 * slot, 2u * kc_all * R * 16);
-            const uint32_t dst = smem_u32(sA) + slot * a.a_slot_bytes;
-            for (int c = 0; c < kc_all; ++c) {
-              const long long plane = (long long)b * (a.c_in / 8) + kb * 8 + c;
-              const long long off = (plane * a.plane_rows + row0) * 8;
-              bulk_g2s(dst + c * R * 16, a.in_hi + off, R * 16, bA_full + 8 * slot);
-              bulk_g2s(dst + aLoOff + c * R * 16, a.in_lo + off, R * 16, bA_full + 8 * slot);
-            }
             if (need_w) {
               mbar_expect_tx(bW_full + 8 * ws, 3 * tapBytes);
               bulk_g2s(smem_u32(sW) + ws * a.w_stage_bytes, a.w + (size_t)sid * 3 * tapBytes, 3 * tapBytes, bW_full + 8 * ws);
             }
+          }
+          __syncwarp();
+          if (lane < 2 * kc_all) {  // one bulk copy per lane (see conv2d_prog.cu: a single issuing lane paced the layer)
+            const int c = lane >> 1, part = lane & 1;
+            const uint32_t dst = smem_u32(sA) + slot * a.a_slot_bytes + (part ? aLoOff : 0u) + c * R * 16;
+            const long long plane = (long long)b * (a.c_in / 8) + kb * 8 + c;
+            const long long off = (plane * a.plane_rows + row0) * 8;
+            bulk_g2s(dst, (part ? a.in_lo : a.in_hi) + off, R * 16, bA_full + 8 * slot);
           }
           __syncwarp();
           ++a_it;

@@ -130,16 +130,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
         const int kc = Cfg::kb_size(kb) / 8;
         const uint32_t slot = a_it % NA, ph = (a_it / NA) & 1;
         mbar_wait(bA_empty + 8 * slot, ph ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(bA_full + 8 * slot, (uint32_t)Cfg::PARTS * kc * kRows * 16);
-          const uint32_t dst = smem_u32(sA) + slot * kASlotBytes;
-          const size_t plane0 = (size_t)b * (C_IN / 8) + kb * 8;
-#pragma unroll
-          for (int c = 0; c < kc; ++c) {
-            const size_t off = ((plane0 + c) * a.npad_in + row0) * 8;
-            bulk_g2s(dst + c * kRows * 16, a.in_hi + off, kRows * 16, bA_full + 8 * slot);
-            if (!FMT) bulk_g2s(dst + kALoOff + c * kRows * 16, a.in_lo + off, kRows * 16, bA_full + 8 * slot);
-          }
+        if (elect_one()) mbar_expect_tx(bA_full + 8 * slot, (uint32_t)Cfg::PARTS * kc * kRows * 16);
+        __syncwarp();
+        if (lane < Cfg::PARTS * kc) {  // one bulk copy per lane: issued back to back by a single lane they cost ~65 cycles each
+          const int c = FMT ? lane : (lane >> 1), part = FMT ? 0 : (lane & 1);
+          const uint32_t dst = smem_u32(sA) + slot * kASlotBytes + (part ? kALoOff : 0) + c * kRows * 16;
+          const size_t off = (((size_t)b * (C_IN / 8) + kb * 8 + c) * a.npad_in + row0) * 8;
+          bulk_g2s(dst, (part ? a.in_lo : a.in_hi) + off, kRows * 16, bA_full + 8 * slot);
         }
         __syncwarp();
         ++a_it;
