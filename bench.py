@@ -292,21 +292,37 @@ def main():
         achieved = dom["flop"] / dom["launches"] / (dur_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         split = 3 if key[3] == "tcgen05 bf16x3" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
-        # DRAM bytes per position from the committed ncu --set full capture (profiles/r01_prof_conv1d.md: 1.024 GB read +
-        # 0.978 GB written for 4.224 M positions of the 64->64 kernel = algorithmic 2 x 64 ch x 4 B planes), scaled to
-        # this run's positions per launch
+        # DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_prof_*.md, dram__bytes_read.sum +
+        # dram__bytes_write.sum), scaled to this run's work per launch:
+        #   decoder_program (118-conv Decoder at batch 2, S = 250): 0.69 GB read + 2.29 GB written per launch -- every layer's
+        #     output map is written back (the rotating activation buffers of two images exceed what L2 keeps dirty)
+        #   conv1d 64->64 fp16x1: 0.512 GB read + 0.471 GB written per 4.224 M positions (= algorithmic 2 x 64 ch x 2 B)
+        #   conv1d 64->64 bf16x3: 1.024 GB + 0.978 GB per 4.224 M positions (r01 capture of the three-product kernel)
         traffic = None
-        if key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 bf16x3":
-            traffic = 474.0 * dom["flop"] / dom["launches"] / (2 * 9 * 64 * 64)
+        per_launch_flop = dom["flop"] / dom["launches"]
+        if key[2] == "decoder_program":
+            traffic = 2.98e9 * per_launch_flop / (2 * 290.5e9)   # ncu launch: 2 maps x 290.5 GFLOP
+        elif key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 fp16x1":
+            traffic = 232.8 * per_launch_flop / (2 * 9 * 64 * 64)
+        elif key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 bf16x3":
+            traffic = 474.0 * per_launch_flop / (2 * 9 * 64 * 64)
+        label = lambda k: ("%s, %d convs (%s)" % (k[2], k[1], k[3])) if k[2] == "decoder_program" else "%s %d->%d (%s)" % (k[2], k[0], k[1], k[3])
+        breakdown = []
+        for k, gk in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+            ach = gk["flop"] / (gk["ms"] * 1e-3) / 1e12
+            sp = 3 if k[3] == "tcgen05 bf16x3" else 1
+            breakdown.append({"kernel": label(k), "ms_per_step": gk["ms"] / args.steps, "launches_per_step": gk["launches"] // args.steps,
+                              "achieved_tflops": ach, "frac": ach / peak, "issued_mma_frac": ach * sp / peak})
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
-                    "kernel": "%s %d->%d (%s)" % (key[2], key[0], key[1], key[3]),
+                    "kernel": label(key),
                     "issued_mma_tflops": achieved * split, "issued_mma_frac": achieved * split / peak,
-                    "note": "achieved = ALGORITHMIC conv FLOP (2*positions*c_in*c_out*9) per launch / launch time; the "
-                            "fp32-parity bf16 hi/lo split issues %dx that many tensor-core FLOP" % split,
+                    "note": "achieved = ALGORITHMIC conv FLOP (2*positions*c_in*c_out*9) per launch / launch time of the kernel with "
+                            "the largest share of the step; it issues %dx that many tensor-core FLOP (%s). `kernels` lists every "
+                            "conv kernel family the same way." % (split, "fp32-parity bf16 hi/lo split" if split == 3 else "single fp16 product"),
                     "avg_launch_ms": dur_ms, "launches_per_step": dom["launches"] // args.steps,
                     "share_of_step": dom["ms"] / args.steps / ms_prof, "ms_per_step_profiled": ms_prof,
-                    "conv_ms_per_step": sum(r["ms"] for r in prof) / args.steps}
+                    "conv_ms_per_step": sum(r["ms"] for r in prof) / args.steps, "kernels": breakdown}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,

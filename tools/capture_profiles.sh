@@ -1,14 +1,19 @@
 #!/bin/bash
-# Run under gpurun (one GPU): launch list of one 4 Mb encoder pass + one decoder cascade, and ncu --set full
-# captures of the three tcgen05 kernels.  Outputs land in gpurun_out/ (post-process with tools/summarise_profiles.py).
+# Run under gpurun (one GPU): launch list of tools/ncu_target.py and ncu --set full captures of every kernel family.
+# The .ncu-rep files are converted to raw-page CSV on the box and deleted (gpurun_out/ is capped at 64 MiB);
+# post-process here with `python tools/summarise_profiles.py r01`.
 set -u
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-    python tools/ncu_target.py > gpurun_out/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:conv1d_tc_kernel -c 8 -f -o gpurun_out/prof_conv1d \
-    python tools/ncu_target.py > gpurun_out/ncu_conv1d.log 2>&1
-NCU_REPS=0 ncu --set full --clock-control none --import-source on -k regex:conv2d_tc_kernel -s 30 -c 6 -f \
-    -o gpurun_out/prof_conv2d python tools/ncu_target.py > gpurun_out/ncu_conv2d.log 2>&1
-ncu --set full --clock-control none -k regex:lconv1_tc -c 1 -f -o gpurun_out/prof_first \
-    python tools/ncu_target.py > gpurun_out/ncu_first.log 2>&1
+T=tools/ncu_target.py
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python $T > gpurun_out/ncu_launches.log 2>&1
+cap() {  # name, kernel regex, launch count
+  ncu --set full --clock-control none -k "regex:$2" -c $3 -f -o /tmp/prof_$1 python $T > gpurun_out/ncu_$1.log 2>&1
+  ncu -i /tmp/prof_$1.ncu-rep --page raw --csv > gpurun_out/prof_$1.csv 2>/dev/null
+  rm -f /tmp/prof_$1.ncu-rep
+}
+cap conv1d conv1d_tc_kernel 16
+cap decoder_program conv2d_program_kernel 2
+cap first lconv1_tc 2
+cap glue "outer_sum_planes|extra_conv_planes|final_head_planes|pool_planes|symmetrise|to_channel_last|from_channel_last|upsample2_planes|lconv1_edge" 16
 for f in gpurun_out/ncu_*.log; do tail -n 1 $f; done
+ls -la gpurun_out

@@ -37,8 +37,9 @@ def launches():
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w") as f:
         f.write("# %s launch list (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
-        f.write("Workload: `tools/ncu_target.py` = ONE 4 Mb Encoder pass (single chunk, all 28 convs) + Encoder2 + one 6-level\n"
-                "decoder cascade (7 decoder calls) of an H1esc-like shell. Cold-cache, serialised launches: compare SHARES.\n\n")
+        f.write("Workload: `tools/ncu_target.py` = one 4 Mb Encoder pass per strand (single chunk, all 7 stages; fp32 one-hot forward\n"
+                "strand, packed-base reverse strand) + Encoder2 + the strand-batched 6-level decoder cascade (7 decoder calls at\n"
+                "batch 2) of an H1esc-like shell. Cold-cache, serialised launches: compare SHARES.\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (n[:110], a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
@@ -46,23 +47,22 @@ def launches():
 
 
 def ncu_raw(name):
-    rep = os.path.join(OUT, name + ".ncu-rep")
-    if not os.path.exists(rep):
-        return
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
-    hdr, units = rows[0], rows[1]
+    path = os.path.join(OUT, name + ".csv")
+    rows = [r for r in csv.reader(open(path)) if r]
+    hi = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    hdr, units = rows[hi], rows[hi + 1]
     with open(os.path.join(ROOT, "profiles", "%s_%s.md" % (tag, name)), "w") as f:
         f.write("# %s %s (ncu --set full --clock-control none), one row per captured launch\n\n" % (tag, name))
         cols = [k for k in KEY if k in hdr]
         f.write("| kernel | " + " | ".join(c.split(".")[0].replace("__", " ") for c in cols) + " |\n")
         f.write("|---|" + "---:|" * len(cols) + "\n")
-        for r in rows[2:]:
+        for r in rows[hi + 2:]:
             kn = r[hdr.index("Kernel Name")]
-            f.write("| `%s` | " % kn[-60:] + " | ".join("%s %s" % (r[hdr.index(c)], units[hdr.index(c)]) for c in cols) + " |\n")
+            f.write("| `%s` | " % kn[-70:] + " | ".join("%s %s" % (r[hdr.index(c)], units[hdr.index(c)]) for c in cols) + " |\n")
 
 
 launches()
-for n in ("prof_conv1d", "prof_conv2d", "prof_first"):
-    ncu_raw(n)
+for fn in sorted(os.listdir(OUT)):
+    if fn.startswith("prof_") and fn.endswith(".csv"):
+        ncu_raw(fn[:-len(".csv")])
 print(os.listdir(os.path.join(ROOT, "profiles")))
