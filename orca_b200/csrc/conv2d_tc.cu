@@ -287,32 +287,43 @@ __device__ __forceinline__ float extra_src2(const float* sb, long long sH, long 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
-__global__ void extra_conv_planes_kernel(const float* __restrict__ src, long long sB, long long sC, long long sH, long long sW,
-                                         int n_extra, const float* __restrict__ w /*[n_extra][9][64]*/,
-                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int S, int Wp,
-                                         long long plane_rows, int mode, long long total) {
+// one thread per pixel: the 9 (upsampled) source values of a channel are evaluated once and feed all 64 outputs
+__global__ void __launch_bounds__(128) extra_conv_planes_kernel(const float* __restrict__ src, long long sB, long long sC, long long sH,
+                                                                long long sW, int n_extra, const float* __restrict__ w /*[n_extra][9][64]*/,
+                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int S, int Wp,
+                                                                long long plane_rows, int mode, long long total) {
+  extern __shared__ float sw[];  // the weights, [n_extra][9][64]
+  for (int i = threadIdx.x; i < n_extra * 9 * 64; i += blockDim.x) sw[i] = __ldg(w + i);
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % S);
-    long long t = i / S;
+    const long long t = i / S;
     const int y = (int)(t % S);
-    t /= S;
-    const int ch = (int)(t % 8);
-    const long long b = t / 8;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long b = t / S;
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
     for (int e = 0; e < n_extra; ++e) {
       const float* sb = src + b * sB + e * sC;
-      const float* we = w + e * 9 * 64;
+      float v[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) v[tp] = extra_src2(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) {
-        const float v = extra_src2(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(we + tp * 64 + ch * 8));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(we + tp * 64 + ch * 8 + 4));
-        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        const float4* wr = reinterpret_cast<const float4*>(sw + (e * 9 + tp) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 w4 = wr[j];  // same address across the warp: shared-memory broadcast
+          acc[4 * j] = fmaf(v[tp], w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v[tp], w4.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v[tp], w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v[tp], w4.w, acc[4 * j + 3]);
+        }
       }
     }
-    const long long off = ((b * 8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
-    split_store8(acc, hi + off, lo + off);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const long long off = ((b * 8 + ch) * plane_rows + (long long)y * Wp + kPX + x) * 8;
+      split_store8(acc + 8 * ch, hi + off, lo + off);
+    }
   }
 }
 
@@ -485,10 +496,13 @@ int tc_outer_sum(const float* xcl, TcMap* out, cudaStream_t s) {
 
 int tc_extra_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra, const float* w_extra,
                   TcMap* out, int mode, cudaStream_t s) {
-  if (out->C != 64 || n_extra < 1) { set_error("tc_extra_conv: C != 64 or no extra channels"); return ORCA_B200_EINVAL; }
-  const long long total = (long long)out->nb * 8 * out->S * out->S;
-  extra_conv_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, sB, sC, sH, sW, n_extra, w_extra, static_cast<__nv_bfloat16*>(out->hi),
-                                                           static_cast<__nv_bfloat16*>(out->lo), out->S, out->Wp, out->plane_rows, mode, total);
+  if (out->C != 64 || n_extra < 1 || n_extra > 8) { set_error("tc_extra_conv: C != 64 or bad extra-channel count"); return ORCA_B200_EINVAL; }
+  const long long total = (long long)out->nb * out->S * out->S;
+  long long grid = (total + 127) / 128;
+  if (grid > 148 * 16) grid = 148 * 16;
+  extra_conv_planes_kernel<<<(unsigned)grid, 128, (size_t)n_extra * 9 * 64 * sizeof(float), s>>>(
+      src, sB, sC, sH, sW, n_extra, w_extra, static_cast<__nv_bfloat16*>(out->hi), static_cast<__nv_bfloat16*>(out->lo), out->S, out->Wp,
+      out->plane_rows, mode, total);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }

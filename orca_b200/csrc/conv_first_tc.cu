@@ -24,15 +24,22 @@ using namespace tcdev;
 
 constexpr int kTaps = 17, kChunks = 10;  // 68 K-elements padded to 80
 
+// F16 = false: operands split into bf16 hi/lo, three products, output as bf16 hi/lo planes (or one fp16 plane).
+// F16 = true (single-pass stage 1): the one-hot input is exact in fp16, the composed weights are rounded to fp16,
+// ONE product per K step, output one fp16 plane; half the shared memory and TMEM columns, so twice the CTAs per SM
+// for this latency-bound (stage, build, multiply, drain) kernel.
+template <bool F16>
 __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long long Ltot, long long l_begin, long long n,
-                                                        int npad, const uint8_t* __restrict__ wimg /*[10][128][16 B]*/,
+                                                        int npad, const uint8_t* __restrict__ wimg /*[10][128 | 64][16 B]*/,
                                                         const float* __restrict__ bias,
                                                         __nv_bfloat16* __restrict__ out_hi,
                                                         __nv_bfloat16* __restrict__ out_lo) {
-  extern __shared__ __align__(128) uint8_t dsm[];  // 3 x 20 KB operand images (dynamic: above the 48 KB static limit)
+  extern __shared__ __align__(128) uint8_t dsm[];  // operand images (dynamic: above the 48 KB static limit)
+  constexpr int kBRows = F16 ? 64 : 128;          // weight rows per K chunk: [B] or [Bh | Bl]
+  constexpr uint32_t kTmemCols = F16 ? 64 : 128;
   uint8_t* sAh = dsm;
-  uint8_t* sAl = dsm + kChunks * 128 * 16;
-  uint8_t* sBw = dsm + 2 * kChunks * 128 * 16;
+  uint8_t* sAl = dsm + kChunks * 128 * 16;  // unused when F16
+  uint8_t* sBw = dsm + (F16 ? 1 : 2) * kChunks * 128 * 16;
   __shared__ float sBias[64];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -44,10 +51,10 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < kChunks * 128; i += 128) reinterpret_cast<uint4*>(sBw)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+  for (int i = tid; i < kChunks * kBRows; i += 128) reinterpret_cast<uint4*>(sBw)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
   if (tid < 64) sBias[tid] = bias[tid];
   tc_fence_before();
   __syncthreads();
@@ -73,8 +80,9 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
     const float4 p0 = *reinterpret_cast<const float4*>(&sX[tid + 2 * j][0]);
     const float4 p1 = *reinterpret_cast<const float4*>(&sX[tid + 2 * j + 1][0]);
     const float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    split_store8(v, reinterpret_cast<__nv_bfloat16*>(sAh + (j * 128 + tid) * 16),
-                 reinterpret_cast<__nv_bfloat16*>(sAl + (j * 128 + tid) * 16));
+    if (F16) store_h8(v, sAh + (j * 128 + tid) * 16);
+    else split_store8(v, reinterpret_cast<__nv_bfloat16*>(sAh + (j * 128 + tid) * 16),
+                      reinterpret_cast<__nv_bfloat16*>(sAl + (j * 128 + tid) * 16));
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -83,14 +91,18 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
 
   if (warp == 0) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(64), idesc_cat = umma_idesc_bf16(128);
+      constexpr uint32_t idesc = umma_idesc_bf16(64), idesc_cat = umma_idesc_bf16(128), idesc16 = umma_idesc_f16(64);
       const uint32_t ah = umma_desc_lo(smem_u32(sAh), 2048), al = umma_desc_lo(smem_u32(sAl), 2048);
-      const uint32_t bw = umma_desc_lo(smem_u32(sBw), 2048);
+      const uint32_t bw = umma_desc_lo(smem_u32(sBw), kBRows * 16);
 #pragma unroll
       for (int ks = 0; ks < kChunks / 2; ++ks) {
-        const uint32_t o = ks * ((2 * 2048) >> 4);
-        umma_bf16(tmem, umma_desc64(ah + o), umma_desc64(bw + o), idesc_cat, ks > 0 ? 1u : 0u);  // [Ah*Bh | Ah*Bl]
-        umma_bf16(tmem, umma_desc64(al + o), umma_desc64(bw + o), idesc, 1u);                    // += Al*Bh
+        const uint32_t o = ks * ((2 * 2048) >> 4), ob = ks * ((2 * kBRows * 16) >> 4);
+        if (F16) {
+          umma_bf16(tmem, umma_desc64(ah + o), umma_desc64(bw + ob), idesc16, ks > 0 ? 1u : 0u);  // fp16 A * fp16 B
+        } else {
+          umma_bf16(tmem, umma_desc64(ah + o), umma_desc64(bw + ob), idesc_cat, ks > 0 ? 1u : 0u);  // [Ah*Bh | Ah*Bl]
+          umma_bf16(tmem, umma_desc64(al + o), umma_desc64(bw + ob), idesc, 1u);                    // += Al*Bh
+        }
       }
       umma_commit(smem_u32(&bar));
     }
@@ -103,11 +115,11 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
   for (int c0 = 0; c0 < 64; c0 += 32) {
     uint32_t r0[32], r1[32];
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r0);
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, r1);
+    if (!F16) tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, r1);
     if (row < n) {
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]) + sBias[c0 + j];
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + (F16 ? 0.f : __uint_as_float(r1[j])) + sBias[c0 + j];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const size_t off = (((size_t)b * 8 + (c0 >> 3) + ch) * npad + row + 4) * 8;
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
 // Exact two-layer evaluation of the 4 positions next to one end of the sequence (see file header).
@@ -234,6 +246,20 @@ int tc_pack_lconv1(ConvLayer& L0, const float* w1, const float* b1, const float*
   L0.tc_w = d;
   L0.tc_w_bytes = img.size() * 2;
   L0.tc_bias = static_cast<float*>(db);
+  // fp16 image of the composed weights for the single-pass variant: [chunk][64 rows][8]
+  std::vector<uint16_t> img16((size_t)kChunks * 64 * 8, 0);
+  for (int j = 0; j < kChunks; ++j)
+    for (int co = 0; co < 64; ++co)
+      for (int e = 0; e < 8; ++e) {
+        const int k = j * 8 + e, t = k / 4, c = k % 4;
+        const __half hv = __float2half_rn(t < kTaps ? (float)wc[((size_t)t * 4 + c) * 64 + co] : 0.f);
+        memcpy(&img16[((size_t)j * 64 + co) * 8 + e], &hv, 2);
+      }
+  void* d16 = nullptr;
+  ORCA_CUDA_OK(cudaMalloc(&d16, img16.size() * 2));
+  allocs.push_back(d16);
+  ORCA_CUDA_OK(cudaMemcpy(d16, img16.data(), img16.size() * 2, cudaMemcpyHostToDevice));
+  L0.tc_w16 = d16;
   return ORCA_B200_OK;
 }
 
@@ -245,19 +271,27 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb,
     return ORCA_B200_EINVAL;
   }
   const long long n_tiles = (n + 127) / 128;
-  dim3 grid((unsigned)(n_tiles < 148 * 3 ? n_tiles : 148 * 3), (unsigned)nb);
-  constexpr int kSmem = 3 * kChunks * 128 * 16;
+  const bool f16 = out->fmt == 1 && L0.tc_w16;
+  if (out->fmt == 1 && !f16) { set_error("tc_lconv1: no fp16 weight image"); return ORCA_B200_EUNSUPPORTED; }
+  const int per_sm = f16 ? 6 : 3;
+  dim3 grid((unsigned)(n_tiles < 148 * per_sm ? n_tiles : 148 * per_sm), (unsigned)nb);
+  constexpr int kSmem = 3 * kChunks * 128 * 16, kSmem16 = kChunks * 128 * 16 + kChunks * 64 * 16;
   static bool configured_dev[32] = {};  // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& configured = configured_dev[cur_dev & 31];
   if (!configured) {
-    ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    ORCA_CUDA_OK(cudaFuncSetAttribute(lconv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem16));
     configured = true;
   }
-  lconv1_tc_kernel<<<grid, 128, kSmem, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
-                                        L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi),
-                                        out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo));
+  if (f16)
+    lconv1_tc_kernel<true><<<grid, 128, kSmem16, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w16),
+                                                    L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), nullptr);
+  else
+    lconv1_tc_kernel<false><<<grid, 128, kSmem, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
+                                                     L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi),
+                                                     out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo));
   ORCA_LAUNCH_OK();
   if (l_begin == 0 || l_begin + n == Ltot) {
     lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,

@@ -69,7 +69,8 @@ struct TcCfg {
   static constexpr int NA = FMT ? 4 : (C_OUT == 64 ? 2 : 3);
   static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
-  static constexpr int SMEM = NA * A_SLOT + NW * STAGE_MAX + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
+  static constexpr int POOL_SCRATCH = FMT ? kEpiWarps * 2048 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
+  static constexpr int SMEM = NA * A_SLOT + NW * STAGE_MAX + POOL_SCRATCH + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
   __host__ __device__ static constexpr int kb_size(int kb) { return (kb == NKB - 1) ? C_IN - 64 * (NKB - 1) : 64; }
   __host__ __device__ static constexpr int stage_bytes(int kb) { return PARTS * (kb_size(kb) / 8) * C_OUT * 16; }
   __host__ __device__ static constexpr int stage_offset(int kb, int tap) {
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + NA * kASlotBytes;
-  float* sBias = reinterpret_cast<float*>(sW + NW * Cfg::STAGE_MAX);
+  uint8_t* sPool = sW + NW * Cfg::STAGE_MAX;
+  float* sBias = reinterpret_cast<float*>(sPool + Cfg::POOL_SCRATCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C_OUT);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NW + 4);
   const uint32_t bA_full = smem_u32(bars), bA_empty = bA_full + 8 * NA;
@@ -284,6 +286,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
         if (c0 + 64 < C_OUT) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
+        }
+        if (FMT && a.pool > 1 && a.out_hi && !a.out_lo) {
+          // Fused max-pool of the single-pass format through shared memory.  TMEM lane = position, so pooling over
+          // 2 / 4 neighbouring positions with warp shuffles costs ~4 instructions per value and made the residual+pool
+          // layers twice as slow as the plain ones (ncu: 567 vs 285 us).  Instead every lane rounds its 32 channels
+          // to fp16 (max commutes with the monotonic rounding), parks them in a [chunk][position][16 B] buffer
+          // (position index XOR-swizzled so that both the writes and the strided reads are bank-conflict free), and
+          // each lane then reduces one (pooled row, 8-channel chunk) with packed fp16 max and stores 16 coalesced bytes.
+          uint8_t* scr = sPool + (warp - 2) * 2048;
+          const int fpos = (lane & ~7) | ((lane ^ (lane >> 3)) & 7);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) store_h8(v + 8 * ch, scr + (ch * 32 + fpos) * 16);
+          __syncwarp();
+          const int P = a.pool, rows = 32 / P;
+          for (int item = lane; item < rows * 4; item += 32) {
+            const int pr = item & (rows - 1), ch = item / rows;
+            __half2 m[4];
+#pragma unroll 1
+            for (int k = 0; k < P; ++k) {
+              const int pos = pr * P + k, sp = (pos & ~7) | ((pos ^ (pos >> 3)) & 7);
+              const uint4 u = *reinterpret_cast<const uint4*>(scr + (ch * 32 + sp) * 16);
+              const __half2* hv = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) m[j] = k == 0 ? hv[j] : __hmax2(m[j], hv[j]);
+            }
+            const size_t orow = (size_t)(t * 128 + q * 32) / P + pr;
+            if (orow < (size_t)a.n_out) {
+              const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_out + orow + 4) * 8;
+              *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(m);
+            }
+          }
+          __syncwarp();
+          continue;
         }
         if (a.pool > 1) {
 #pragma unroll
