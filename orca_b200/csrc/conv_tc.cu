@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(bA_full + 8 * i, 1); mbar_init(bA_empty + 8 * i, 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(bW_full + 8 * i, 1); mbar_init(bW_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, 32 * kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bAcc_full + 8 * i, 1); mbar_init(bAcc_empty + 8 * i, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
         }
       }
       tc_fence_before();
-      mbar_arrive(bAcc_empty + 8 * as);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bAcc_empty + 8 * as);  // one arrival per warp: 256 same-word atomics per tile serialise
       ++acc_it;
     }
   }
