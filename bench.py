@@ -268,6 +268,20 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = 2 * L / (ms_e2e * 1e-3) / 1e6
+    h2d_fp32 = int(runner.h2d_bytes)
+
+    # the same end-to-end step fed with packed bases (1 B/bp, orca_b200.feeder) instead of the reference's fp32 one-hot
+    codes_host = torch.from_numpy(synthetic.random_codes(1, L, 0)).pin_memory()
+
+    def step_e2e_packed():
+        runner.upload(codes_host)
+        maps = runner.forward(mpos, wpos)
+        return maps.cpu() if maps is not None else None
+
+    step_e2e_packed()
+    ms_e2e_packed = timed(step_e2e_packed, args.steps) / args.steps
+    h2d_packed = int(runner.h2d_bytes)
+    runner.upload(seq_host)  # back to the fp32 window for the roofline leg
 
     # roofline leg: same steps with per-launch CUDA events around every conv kernel
     _lib.profile_enable(True)
@@ -341,7 +355,10 @@ def main():
                 "contact_maps_per_s": maps_per_step / (ms_step * 1e-3),
                 "algorithmic_tflops": 2 * flop_per_strand / (ms_step * 1e-3) / 1e12,
                 "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": int(runner.h2d_bytes), "d2h_bytes_per_step": int(runner.d2h_bytes)},
+                        "h2d_bytes_per_step": h2d_fp32, "d2h_bytes_per_step": int(runner.d2h_bytes),
+                        "packed_bases": {"value": 2 * L / (ms_e2e_packed * 1e-3) / 1e6, "ms_per_step": ms_e2e_packed,
+                                         "h2d_bytes_per_step": h2d_packed,
+                                         "note": "same step with the sequence uploaded as 1 B/bp packed bases (orca_b200.feeder)"}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

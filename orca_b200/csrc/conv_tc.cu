@@ -65,12 +65,19 @@ struct TcCfg {
   static constexpr int PARTS = FMT ? 1 : 2;               // operand images per K chunk
   static constexpr int A_SLOT = PARTS * 8 * kRows * 16;   // one 64-channel K-block of a tile
   static constexpr int STAGE_MAX = PARTS * 8 * C_OUT * 16;  // weights of one (64-channel K-block, tap)
-  static constexpr int NW = FMT ? (C_OUT == 128 ? 6 : 9) : (C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3));
-  static constexpr int NA = FMT ? 4 : (C_OUT == 64 ? 2 : 3);
+  // single-pass 96 -> 96: all 18 (K-block, tap) stages stay resident (166 KB).  Re-streaming them for every tile made the
+  // layer shared-memory-bandwidth bound (writes of 166 KB + operand reads of ~380 KB per tile through one 128 B/clk port).
+  static constexpr bool BIG_RESIDENT = FMT && C_IN == 96 && C_OUT == 96;
+  static constexpr int NW = BIG_RESIDENT ? 18 : FMT ? (C_OUT == 128 ? 6 : 9) : (C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3));
+  static constexpr int NA = BIG_RESIDENT ? 3 : FMT ? 4 : (C_OUT == 64 ? 2 : 3);
+  static constexpr int POOL_CHUNKS = BIG_RESIDENT ? 2 : 4;  // 8-channel chunks per pass of the fused max-pool buffer
   static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
-  static constexpr int POOL_SCRATCH = FMT ? kEpiWarps * 2048 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
-  static constexpr int SMEM = NA * A_SLOT + NW * STAGE_MAX + POOL_SCRATCH + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
+  static constexpr int POOL_SCRATCH = FMT ? kEpiWarps * POOL_CHUNKS * 512 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
+  // resident stages are packed back to back (a 32-channel K-block's stages are half size), streamed ones use a ring of
+  // full-size slots
+  static constexpr int W_BYTES = RESIDENT ? 9 * PARTS * (C_IN / 8) * C_OUT * 16 : NW * STAGE_MAX;
+  static constexpr int SMEM = NA * A_SLOT + W_BYTES + POOL_SCRATCH + C_OUT * 4 + (2 * NA + 2 * NW + 4) * 8 + 16 + 128;
   __host__ __device__ static constexpr int kb_size(int kb) { return (kb == NKB - 1) ? C_IN - 64 * (NKB - 1) : 64; }
   __host__ __device__ static constexpr int stage_bytes(int kb) { return PARTS * (kb_size(kb) / 8) * C_OUT * 16; }
   __host__ __device__ static constexpr int stage_offset(int kb, int tap) {
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + NA * kASlotBytes;
-  uint8_t* sPool = sW + NW * Cfg::STAGE_MAX;
+  uint8_t* sPool = sW + Cfg::W_BYTES;
   float* sBias = reinterpret_cast<float*>(sPool + Cfg::POOL_SCRATCH);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + C_OUT);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA + 2 * NW + 4);
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
           if (!RESIDENT) mbar_wait(bW_empty + 8 * ws, wph ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bW_full + 8 * ws, Cfg::stage_bytes(kb));
-            bulk_g2s(smem_u32(sW) + ws * Cfg::STAGE_MAX, a.w + Cfg::stage_offset(kb, tap), Cfg::stage_bytes(kb),
-                     bW_full + 8 * ws);
+            bulk_g2s(smem_u32(sW) + (RESIDENT ? (uint32_t)Cfg::stage_offset(kb, tap) : ws * Cfg::STAGE_MAX),
+                     a.w + Cfg::stage_offset(kb, tap), Cfg::stage_bytes(kb), bW_full + 8 * ws);
           }
           __syncwarp();
           ++w_it;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
           if (!RESIDENT || ti == 0) mbar_wait(bW_full + 8 * ws, RESIDENT ? 0u : ((w_it / NW) & 1));
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t bLo = umma_desc_lo(smem_u32(sW) + ws * Cfg::STAGE_MAX, bLbo);
+            const uint32_t bLo = umma_desc_lo(smem_u32(sW) + (RESIDENT ? (uint32_t)Cfg::stage_offset(kb, tap) : ws * Cfg::STAGE_MAX), bLbo);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               if (ks < ksteps) {
@@ -294,30 +301,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
           // to fp16 (max commutes with the monotonic rounding), parks them in a [chunk][position][16 B] buffer
           // (position index XOR-swizzled so that both the writes and the strided reads are bank-conflict free), and
           // each lane then reduces one (pooled row, 8-channel chunk) with packed fp16 max and stores 16 coalesced bytes.
-          uint8_t* scr = sPool + (warp - 2) * 2048;
+          constexpr int CHP = Cfg::POOL_CHUNKS;  // chunks per pass (the buffer holds CHP x 32 positions x 16 B per warp)
+          uint8_t* scr = sPool + (warp - 2) * (CHP * 512);
           const int fpos = (lane & ~7) | ((lane ^ (lane >> 3)) & 7);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) store_h8(v + 8 * ch, scr + (ch * 32 + fpos) * 16);
-          __syncwarp();
           const int P = a.pool, rows = 32 / P;
-          for (int item = lane; item < rows * 4; item += 32) {
-            const int pr = item & (rows - 1), ch = item / rows;
-            __half2 m[4];
-#pragma unroll 1
-            for (int k = 0; k < P; ++k) {
-              const int pos = pr * P + k, sp = (pos & ~7) | ((pos ^ (pos >> 3)) & 7);
-              const uint4 u = *reinterpret_cast<const uint4*>(scr + (ch * 32 + sp) * 16);
-              const __half2* hv = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) m[j] = k == 0 ? hv[j] : __hmax2(m[j], hv[j]);
+          for (int pass = 0; pass < 4 / CHP; ++pass) {
+#pragma unroll
+            for (int ch = 0; ch < CHP; ++ch) store_h8(v + 8 * (pass * CHP + ch), scr + (ch * 32 + fpos) * 16);
+            __syncwarp();
+            for (int item = lane; item < rows * CHP; item += 32) {
+              const int pr = item & (rows - 1), ch = item / rows;
+              __half2 m[4];
+#pragma unroll 1
+              for (int k = 0; k < P; ++k) {
+                const int pos = pr * P + k, sp = (pos & ~7) | ((pos ^ (pos >> 3)) & 7);
+                const uint4 u = *reinterpret_cast<const uint4*>(scr + (ch * 32 + sp) * 16);
+                const __half2* hv = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = k == 0 ? hv[j] : __hmax2(m[j], hv[j]);
+              }
+              const size_t orow = (size_t)(t * 128 + q * 32) / P + pr;
+              if (orow < (size_t)a.n_out) {
+                const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + pass * CHP + ch) * a.npad_out + orow + 4) * 8;
+                *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(m);
+              }
             }
-            const size_t orow = (size_t)(t * 128 + q * 32) / P + pr;
-            if (orow < (size_t)a.n_out) {
-              const size_t off = (((size_t)b * (C_OUT / 8) + (c0 >> 3) + ch) * a.npad_out + orow + 4) * 8;
-              *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(m);
-            }
+            __syncwarp();
           }
-          __syncwarp();
           continue;
         }
         if (a.pool > 1) {

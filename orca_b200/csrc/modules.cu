@@ -871,8 +871,6 @@ static int check_ptr_device(const void* p, const char* what) {
 
 }  // namespace orca
 
-namespace orca { long long* tc2d_trace_buffer(); }  // conv2d_prog.cu (diagnostic event trace)
-
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -1181,15 +1179,6 @@ int64_t orca_b200_profile_summary(char* buf, int64_t cap) {
   js += "]";
   if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", js.c_str()); }
   return (int64_t)js.size() + 1;
-}
-
-// ---- diagnostics -----------------------------------------------------------------------------
-// copies the decoder-program event trace of the last launch (env ORCA_B200_DEC_TRACE) into out[4 * 2048]; returns 0 if none
-int orca_b200_debug_trace(long long* out) {
-  long long* d = orca::tc2d_trace_buffer();
-  if (!d || !out) return 0;
-  if (cudaMemcpy(out, d, 4 * 2048 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return 4 * 2048;
 }
 
 // ---- background ------------------------------------------------------------------------------

@@ -77,6 +77,16 @@ def random_sequence(batch, length, seed, n_fraction=0.0):
     return seq
 
 
+def random_codes(batch, length, seed, n_fraction=0.0):
+    """The same sequence as random_sequence(batch, length, seed, n_fraction) as packed codes (B, L) uint8:
+    0..3 = A, C, G, T, 4 = N (orca_b200.feeder); feeder.to_onehot(random_codes(...)) == random_sequence(...)."""
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, 4, size=(batch, length)).astype(np.uint8)
+    if n_fraction > 0:
+        codes[rng.random((batch, length)) < n_fraction] = 4
+    return codes
+
+
 def expected_log(n=8000):
     """Synthetic log expected-contact curve e[d] = -0.8 ln(d + 1) - 3."""
     return -0.8 * np.log(np.arange(n, dtype=np.float64) + 1.0) - 3.0
