@@ -86,14 +86,14 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------
 # reference algorithm on the host CPU (oracle port; test/baseline infrastructure)
 # ----------------------------------------------------------------------------------------------------
-CPU_BLOCKS = 6   # encoder blocks per CPU sample (of the 40 per strand at 32 Mb)
-CPU_DECODERS = 2  # Decoder calls per CPU sample (of the 6 per strand)
+CPU_BLOCKS = 20  # encoder blocks per CPU sample (of the 40 per strand at 32 Mb)
+CPU_DECODERS = 6  # Decoder calls per CPU sample (all 6 of a strand)
 CPU_SAMPLE = ("%d of 40 encoder blocks per strand (912 kb each incl. the 112 kb halo), Encoder2@8000, %d of 6 Decoder calls, "
               "Decoder_1m" % (CPU_BLOCKS, CPU_DECODERS))
 
 
 def cpu_sample(threads):
-    """Time a bounded sample (~10-20 s of CPU work) of the workload with the oracle port on `threads` host threads
+    """Time a bounded sample (~10-20 s of CPU work on a 16-core host) of the workload with the oracle port on `threads` host threads
     and extrapolate to one full step.  Sample: CPU_BLOCKS 800 kb encoder blocks with their 112 kb halo
     (orca_modules.py:957-977), Encoder2 on 8000 bins, CPU_DECODERS Decoder calls and one Decoder_1m call; returns
     per-unit seconds (block, Encoder2, Decoder, Decoder_1m)."""

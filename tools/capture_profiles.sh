@@ -11,9 +11,9 @@ cap() {  # name, kernel regex, launch count
   ncu -i /tmp/prof_$1.ncu-rep --page raw --csv > gpurun_out/prof_$1.csv 2>/dev/null
   rm -f /tmp/prof_$1.ncu-rep
 }
-cap conv1d conv1d_tc_kernel 16
-cap decoder_program conv2d_program_kernel 2
+cap conv1d conv1d_tc_kernel 11
+cap decoder_program conv2d_program_kernel 1
 cap first lconv1_tc 2
-cap glue "outer_sum_planes|extra_conv_planes|final_head_planes|pool_planes|symmetrise|to_channel_last|from_channel_last|upsample2_planes|lconv1_edge" 16
+cap glue "extra_conv_planes|outer_sum_planes|final_head_planes|pool_planes" 6
 for f in gpurun_out/ncu_*.log; do tail -n 1 $f; done
 ls -la gpurun_out
