@@ -38,13 +38,16 @@ MAPS_PER_STEP = 12                    # raw decoder maps per step (6 levels x 2 
 
 
 def load_peaks():
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as f:
             p = json.load(f)
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
-                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+        burst = float(p["bf16_tflops"])
+        return {"hbm_gbs": float(p.get("hbm_gbs", fallback["hbm_gbs"])), "bf16_tflops": burst,
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", burst)), "source": "measured"}
+    except (OSError, ValueError, KeyError, TypeError):
+        return fallback
 
 
 class ClockSampler(threading.Thread):
