@@ -25,7 +25,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             e1.record()
             torch.cuda.synchronize()
         out.append("B=%d %.3f ms (%.2f us/conv)" % (B, e0.elapsed_time(e1) / 5, e0.elapsed_time(e1) / 5 * 1e3 / 118))
-    print("experiment=%s tma=%s: %s" % (os.environ.get("ORCA_B200_DEC_EXPERIMENT", "0"), os.environ.get("ORCA_B200_DEC_TMA", "1"), " | ".join(out)))
+    print("experiment=%s: %s" % (os.environ.get("ORCA_B200_DEC_EXPERIMENT", "0"), " | ".join(out)))
 else:
     exps = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 9, 3, 6, 7, 15]
     for exp in exps:
