@@ -328,7 +328,8 @@ static SeqIn seq_at(const SeqIn& x, int64_t b) {
 }
 
 static const int64_t kBin = 4000, kHaloBins = 28;  // x_padding = 112000, orca_modules.py:931-932
-static const int64_t kDefaultChunkBp = 16000000;  // ~13.5 GB of workspace; 2 chunks per 32 Mb strand
+static const int64_t kDefaultChunkBp = 32000000;  // ~27 GB of workspace (of 180 GB); a 32 Mb strand is one chunk: no halo
+                                                  // recompute and the small late-stage kernels launch once per strand
 
 static int encoder_run(const orca_b200_module* m, const SeqIn& x, int64_t B, int64_t L, float* out, int64_t bin_begin,
                        int64_t bin_end, int64_t chunk_bp, Arena& ar, cudaStream_t s) {

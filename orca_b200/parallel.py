@@ -188,6 +188,16 @@ class ShardedForward:
                 return torch.stack([t[0] for t in p], 0)  # (n_maps, C, 250, 250)
 
             if world == 1 and self.cascade_mode == "batch":
+                # the U-nets of the two strands as one batch-2 call (their ~40 small launches per call are latency-bound)
+                both_enc = torch.cat([enc_f, enc_r], 0)
+                if is256:
+                    outs = shell.net(shell.net1(both_enc, coarsest_only=True)[-1])
+                    levels = [32, 64, 128, 256]
+                else:
+                    outs = shell.net(both_enc)
+                    levels = [1, 2, 4, 8, 16, 32]
+                for i, rev in enumerate((False, True)):
+                    nets[rev] = {lvl: t[i:i + 1] for lvl, t in zip(levels, outs)}
                 lanes = [(finest(False), False), (finest(True), True)]
                 if is256:
                     if self.background is None:
