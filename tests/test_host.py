@@ -109,6 +109,29 @@ def test_module_create_validates_architecture():
     assert lib.orca_b200_set_impl(7) == -1
 
 
+def test_abi_argument_checks_without_a_gpu():
+    """Entry points that validate before touching the device: the multi-map module spec (num_2d read off the final
+    conv), the region arithmetic of the background assembly, the packed-input stride check."""
+    lib = _lib.lib()
+    handle = ctypes.c_void_p()
+    # a Decoder table whose final conv claims 9 maps: outside [1, 8]
+    arr = (_lib.ConvParams * 122)()
+    arr[113].c_out = 9
+    assert lib.orca_b200_module_create(_lib.DECODER, arr, 122, 0, 0, ctypes.byref(handle)) == -1
+    assert b"num_2d" in lib.orca_b200_last_error()
+    # region arithmetic: int((end - start) / binsize) bins per region, as orca_predict.py:948-957 counts them
+    regs = (_lib.Region * 3)()
+    for r, (c, s0, e0, rv) in zip(regs, [(0, 0, 3_200_000, 0), (0, 8_000_000, 9_600_000, 1), (1, 40_000_000, 40_816_000, 1)]):
+        r.chrom, r.start, r.end, r.reverse = c, s0, e0, rv
+    assert lib.orca_b200_background_bins(regs, 3, 32000) == 100 + 50 + 25
+    regs[1].end = regs[1].start
+    assert lib.orca_b200_background_bins(regs, 3, 32000) == -1 and b"empty" in lib.orca_b200_last_error()
+    # packed encoder input with a zero position stride is rejected before any pointer is looked at
+    assert lib.orca_b200_encoder_forward_packed(None, None, 1, 4000, 4000, 0, 0, 0, 4000, None, 0, 1, 0, None, 0, None) == -1
+    assert lib.orca_b200_set_encoder_fp16_stages(-1) == 3  # default: stages 1-3 single-pass
+    assert lib.orca_b200_set_encoder_fp16_stages(-1) == 3
+
+
 def test_synthetic_is_deterministic():
     a = synthetic.fill_state_dict(modules.Encoder2b().state_dict(), 5)
     b = synthetic.fill_state_dict(modules.Encoder2b().state_dict(), 5)
