@@ -55,7 +55,14 @@ class Shell(nn.Module):
 
 
 def _strip(sd, prefix="module."):
-    return {(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in sd.items()}
+    """Drop every leading "module." (nn.DataParallel / AveragedModel wrappers): the reference's stage-a file carries
+    the prefix twice (orca_models.py:111 indexes it with "module." + a DataParallel key), the others once."""
+    out = {}
+    for k, v in sd.items():
+        while k.startswith(prefix):
+            k = k[len(prefix):]
+        out[k] = v
+    return out
 
 
 def _load_file(path):
@@ -94,7 +101,8 @@ def build_shell(classes, kind="h1esc", seed=0, orca_path=None):
                                   "orca_%s.net0.statedict" % cell, True)
         sh.normmats, sh.epss = _background_32mb(orca_path, cell)
     elif kind in ("h1esc_1m", "hff_1m"):
-        sh.net = _init(classes.Net(num_1d=32), base + _SEED_NET0, orca_path, "orca_%s.net0.statedict" % cell, True)
+        num_1d = 32 if cell == "h1esc" else 22  # orca_models.py:468 (H1esc_1M) / :516 (Hff_1M)
+        sh.net = _init(classes.Net(num_1d=num_1d), base + _SEED_NET0, orca_path, "orca_%s.net0.statedict" % cell, True)
         mats, epss = _background_32mb(orca_path, cell, res1000=True)
         sh.normmats, sh.epss = mats, epss
     elif kind in ("h1esc_256m", "hff_256m"):
@@ -124,7 +132,8 @@ def build_shell(classes, kind="h1esc", seed=0, orca_path=None):
     return sh
 
 
-_RES = {"h1esc": "4DNFI9GMP2J8", "hff": "4DNFI643OYP9", "hctnoc": "4DNFILP99QJS"}
+# resource file stems (orca_models.py:136, :295, :408)
+_RES = {"h1esc": "4DNFI9GMP2J8", "hff": "4DNFI643OYP9", "hctnoc": "4DNFILP99QJS.HCT_auxin6h"}
 
 
 def _background_32mb(orca_path, cell, res1000=False):
