@@ -235,6 +235,10 @@ int orca_b200_net_forward_packed(const orca_b200_module* m, const uint8_t* bases
  */
 int orca_b200_background_forward(const double* normmat, int64_t n, int64_t r0, int64_t f,
                                  int64_t S, int32_t flip, float* out, void* stream);
+/* Same, and additionally (out_mean != NULL) the float64 block nanmean itself, (S, S) row-major and NOT flipped: the
+ * matrices genomepredict_256Mb returns as output['normmats'] (orca_predict.py:724-737). */
+int orca_b200_background_level(const double* normmat, int64_t n, int64_t r0, int64_t f, int64_t S,
+                               int32_t flip, float* out_log, double* out_mean, void* stream);
 
 /*
  * Background matrix of a multi-region 256 Mb input, assembled on the device -- replaces the normmat branch of

@@ -271,6 +271,111 @@ def main():
             save("genomepredict_32mb_leukemia", shell_seed=9, seq_seed=109, mpos=mpos, wpos=wpos, predictions=preds,
                  start_coords=np.asarray(res["start_coords"], dtype=np.int64))
 
+        # ---------------- cascade index math at the edges (fake networks, unmodified drivers) ----------------
+        if want("cascade_index_cases"):
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import fakes
+            out = {}
+            sh = fakes.FakeShell("h1esc")
+            seq = fakes.stub_sequence(32000000, 111)
+            for i, (mpos, wpos) in enumerate(fakes.CASES_32MB):
+                res = op.genomepredict(seq, "chrS", mpos, wpos, models=[sh], use_cuda=False)
+                out["p32_%d" % i] = np.stack(res["predictions"][0]).astype(np.float32)[:, ::5, ::5]  # subsampled: keeps the fixture small
+                out["s32_%d" % i] = np.asarray(res["start_coords"], dtype=np.int64)
+                print("cascade 32 Mb case", i, mpos, wpos, res["start_coords"])
+            sh = fakes.FakeShell("h1esc_256m")
+            seq = fakes.stub_sequence(64000, 112)
+            for i, (mpos, wpos, chrlen) in enumerate(fakes.CASES_256MB):
+                nm = synthetic.normmat_256mb(chrlen_bins=min(8000, chrlen // 32000))
+                res = op.genomepredict_256Mb(seq, "chrS", [nm], chrlen, mpos, wpos, models=[sh], use_cuda=False)
+                out["p256_%d" % i] = np.stack(res["predictions"][0]).astype(np.float32)[:, ::5, ::5]
+                out["s256_%d" % i] = np.asarray(res["start_coords"], dtype=np.int64)
+                out["e256_%d" % i] = np.asarray(res["end_coords"], dtype=np.int64)
+                out["n256_%d" % i] = np.stack([np.stack([ns[l][0] for l in (256, 128, 64, 32)]) for ns in res["normmats"]])[:, :, ::10, ::10]
+                print("cascade 256 Mb case", i, mpos, wpos, chrlen, res["start_coords"])
+            save("cascade_index_cases", seq32_seed=111, seq256_seed=112, **out)
+
+        # ---------------- Orca-1Mb at full size (README screen path) ----------------
+        if want("net_1mb"):
+            t0 = time.time()
+            m = ref_module(om.Net, 18, num_1d=32)
+            x = torch.from_numpy(synthetic.random_sequence(1, 1000000, 113, 0.001)).transpose(1, 2)
+            pred, p1d = m(x)
+            print("net_1mb", pred.shape, p1d.shape, "absmax %.3f" % pred.abs().max(), "%.0fs" % (time.time() - t0))
+            save("net_1mb", weight_seed=18, L=1000000, B=1, seq_seed=113, n_fraction=0.001, num_1d=32, out=pred.numpy(), out_1d=p1d.numpy())
+
+        # ---------------- batch 4 ----------------
+        if want("encoder_b4_24k"):
+            m = ref_module(om.Encoder, 19)
+            x = torch.from_numpy(synthetic.random_sequence(4, 24000, 114, 0.02)).transpose(1, 2)
+            y = m(x).numpy()
+            save("encoder_b4_24k", weight_seed=19, L=24000, B=4, seq_seed=114, n_fraction=0.02, out=y)
+        if want("decoder_b4_40"):
+            m = ref_module(om.Decoder, 20, upsample_mode="bilinear")
+            x = randn((4, 128, 40), 321, 0.5)
+            distenc = randn((4, 1, 40, 40), 322)
+            yc = randn((4, 1, 20, 20), 323)
+            y = m(x, distenc, yc).numpy()
+            save("decoder_b4_40", weight_seed=20, mode="bilinear", S=40, B=4, x_seed=321, d_seed=322, y_seed=323, out=y)
+
+        # ---------------- hard inputs / weights for the single-pass fp16 encoder stages ----------------
+        for name, recipe, seqkind in [("encoder_hard_alln", "default", "alln"), ("encoder_hard_homopolymer", "default", "homopolymer"),
+                                      ("encoder_hard_nruns", "default", "nruns"), ("encoder_hard_widebn", "wide_bn", "random"),
+                                      ("encoder_hard_heavytail", "heavy_tail", "random")]:
+            if not want(name):
+                continue
+            m = om.Encoder()
+            m.load_state_dict(synthetic.fill_state_dict(m.state_dict(), 21, recipe=recipe))
+            m.eval()
+            x = torch.from_numpy(synthetic.hard_sequence(1, 96000, 115, seqkind)).transpose(1, 2)
+            y = m(x).numpy()
+            print(name, y.shape, "absmax %.4g" % np.abs(y).max(), "finite", bool(np.isfinite(y).all()))
+            save(name, weight_seed=21, recipe=recipe, seqkind=seqkind, L=96000, seq_seed=115, out=y)
+
+        # ---------------- HCTnoc-like shell through the unmodified driver (Encoder2b, nearest, no Decoder_1m) ----------------
+        if want("genomepredict_32mb_hctnoc") and args.big:
+            t0 = time.time()
+            shell = models.build_shell(om, "hctnoc", seed=12)
+
+            # orca_predict.genomepredict adds model.denet_1_pt at the 1 Mb level unconditionally (orca_predict.py:356-366),
+            # which the reference HCTnoc shell does not have (orca_models.py:335-446): as written, the unmodified driver
+            # raises AttributeError on it.  The fixture runs the driver with a ZERO Decoder_1m term attached, i.e. the
+            # HCTnoc cascade as its networks define it; orca_b200.predict skips the term when the shell has none.
+            class Zero1m(torch.nn.Module):
+                def forward(self, x):
+                    return torch.zeros((x.shape[0], 1, x.shape[2], x.shape[2]))
+            shell.denet_1_pt = Zero1m()
+            seq = synthetic.random_sequence(1, 32000000, 116)
+            mpos, wpos = 3100000, 16000000   # zooms towards the left edge: start_index clips to 0 at the fine levels
+            res = op.genomepredict(seq, "chrS", mpos, wpos, models=[shell], use_cuda=False)
+            preds = np.stack(res["predictions"][0]).astype(np.float32)
+            print("genomepredict_32mb_hctnoc", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
+            save("genomepredict_32mb_hctnoc", shell_seed=12, seq_seed=116, mpos=mpos, wpos=wpos, predictions=preds,
+                 start_coords=np.asarray(res["start_coords"], dtype=np.int64))
+
+        if want("genomepredict_256mb_stub2"):
+            # as genomepredict_256mb_stub, with a stub net0 that DEPENDS on its input (so the two strands differ),
+            # a chromosome shorter than the window and an off-centre zoom; also keeps output['normmats']
+            t0 = time.time()
+            shell = models.build_shell(om, "h1esc_256m", seed=13)
+
+            class StubNet0(torch.nn.Module):
+                def forward(self, x):  # (B, 4, 64000): one input position per 4 kb bin
+                    w = torch.from_numpy(np.random.default_rng(117).standard_normal((128, 4)).astype(np.float32))
+                    e = torch.einsum("kc,bcl->bkl", w, x)
+                    return 0.5 * (e + 0.5 * torch.roll(e, 1, 2) + 0.25 * torch.roll(e, -3, 2))
+            shell.net0 = StubNet0()
+            seq = synthetic.random_sequence(1, 64000, 118, 0.01)
+            nm = synthetic.normmat_256mb(chrlen_bins=5000)
+            mpos, wpos, chrlen = 40000000, 128000000, 5000 * 32000
+            res = op.genomepredict_256Mb(seq, "chrS", [nm.copy()], chrlen, mpos, wpos, models=[shell], use_cuda=False)
+            preds = np.stack(res["predictions"][0]).astype(np.float32)
+            nms = np.stack([np.stack([ns[l][0] for l in (256, 128, 64, 32)]) for ns in res["normmats"]])
+            print("genomepredict_256mb_stub2", preds.shape, res["start_coords"], "%.0fs" % (time.time() - t0))
+            save("genomepredict_256mb_stub2", shell_seed=13, w_seed=117, seq_seed=118, chrlen_bins=5000, mpos=mpos, wpos=wpos,
+                 chrlen=chrlen, predictions=preds, start_coords=np.asarray(res["start_coords"], dtype=np.int64),
+                 end_coords=np.asarray(res["end_coords"], dtype=np.int64), normmats=nms)
+
         if want("genomepredict_256mb_stub"):
             # Driver logic of genomepredict_256Mb with a stub net0 (a seeded random 4 kb encoding), so the
             # fixture exercises net1(...)[-1], Encoder3, the background levels and the cascade index math

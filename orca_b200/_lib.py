@@ -65,6 +65,7 @@ SIGNATURES = {
     "orca_b200_net_forward_packed": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp, _vp,
                                                     ctypes.c_size_t, _vp]),
     "orca_b200_background_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp]),
+    "orca_b200_background_level": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, ctypes.c_int32, _vp, _vp, _vp]),
     "orca_b200_background_bins": (ctypes.c_int64, [ctypes.POINTER(Region), ctypes.c_int32, _i64]),
     "orca_b200_background_assemble": (ctypes.c_int, [ctypes.POINTER(Region), ctypes.c_int32, _vp, _i64, ctypes.c_double, _i64,
                                                      _vp, _i64, _vp, ctypes.c_size_t, _vp]),

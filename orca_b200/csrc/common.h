@@ -106,7 +106,7 @@ int head_1d_sigmoid(const float* in, const ConvLayer& L, float* out, int B, int 
 int copy_f32(const float* src, float* dst, int64_t n, cudaStream_t s);
 
 int background_level(const double* normmat, int64_t n, int64_t r0, int64_t f, int64_t S, int flip,
-                     float* out, cudaStream_t s);
+                     float* out, double* out_mean, cudaStream_t s);
 int background_assemble(const double* coord, const int* chrom, const double* cis, double trans, double binsize,
                         double* out, int64_t n, cudaStream_t s);
 

@@ -329,7 +329,8 @@ int copy_f32(const float* src, float* dst, int64_t n, cudaStream_t s) {
 // One warp per output cell; lanes stride the f columns of each block row (coalesced fp64 reads),
 // warp-shuffle reduction per row, then the row means are averaged.
 __global__ void background_level_kernel(const double* __restrict__ nm, long long n, long long r0,
-                                        long long f, int S, int flip, float* __restrict__ out) {
+                                        long long f, int S, int flip, float* __restrict__ out,
+                                        double* __restrict__ out_mean) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= (long long)S * S) return;
@@ -355,18 +356,19 @@ __global__ void background_level_kernel(const double* __restrict__ nm, long long
     const double m = rcnt > 0 ? rsum / (double)rcnt : nan("");
     const int oi = flip ? S - 1 - i : i, oj = flip ? S - 1 - j : j;
     out[(long long)oi * S + oj] = logf((float)m);
+    if (out_mean) out_mean[(long long)i * S + j] = m;  // the un-flipped float64 block mean (output['normmats'], :729-737)
   }
 }
 
 int background_level(const double* normmat, int64_t n, int64_t r0, int64_t f, int64_t S, int flip,
-                     float* out, cudaStream_t s) {
+                     float* out, double* out_mean, cudaStream_t s) {
   if (n <= 0 || f <= 0 || S <= 0 || r0 < 0 || r0 + S * f > n) {
     set_error("background_forward: window [%lld, %lld) outside the (%lld x %lld) matrix", (long long)r0,
               (long long)(r0 + S * f), (long long)n, (long long)n);
     return ORCA_B200_EINVAL;
   }
   const long long warps = (long long)S * S;
-  background_level_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(normmat, n, r0, f, (int)S, flip, out);
+  background_level_kernel<<<blocks_for(warps, 8), 256, 0, s>>>(normmat, n, r0, f, (int)S, flip, out, out_mean);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }

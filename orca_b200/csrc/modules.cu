@@ -1187,7 +1187,15 @@ int orca_b200_background_forward(const double* normmat, int64_t n, int64_t r0, i
                                  float* out, void* stream) {
   ORCA_TRY(check_ptr_device(normmat, "background: normmat"));
   ORCA_TRY(check_ptr_device(out, "background: out"));
-  return background_level(normmat, n, r0, f, S, flip, out, static_cast<cudaStream_t>(stream));
+  return background_level(normmat, n, r0, f, S, flip, out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int orca_b200_background_level(const double* normmat, int64_t n, int64_t r0, int64_t f, int64_t S, int32_t flip,
+                               float* out_log, double* out_mean, void* stream) {
+  ORCA_TRY(check_ptr_device(normmat, "background: normmat"));
+  ORCA_TRY(check_ptr_device(out_log, "background: out_log"));
+  if (out_mean) ORCA_TRY(check_ptr_device(out_mean, "background: out_mean"));
+  return background_level(normmat, n, r0, f, S, flip, out_log, out_mean, static_cast<cudaStream_t>(stream));
 }
 
 // Multi-region background matrix (orca_predict.py:936-965).  Per region the reference takes

@@ -53,21 +53,62 @@ def _to_device_sequence(sequence, device):
         t = sequence.float().contiguous()
     if t.dim() != 3 or t.size(2) != 4:
         raise ValueError("sequence must be (B, L, 4), got %s" % (tuple(t.shape),))
-    return t.to(device, non_blocking=True)
+    if t.is_cuda or t.is_pinned() or torch.device(device).type != "cuda" or t.numel() * 4 < (_STAGE_BYTES << 1):
+        return t.to(device, non_blocking=True)
+    return _upload_pageable(t, device)
+
+
+_STAGE_BYTES = 32 << 20
+_STAGING = {}
+
+
+def _upload_pageable(t, device):
+    """Pageable host tensor -> device through two pinned staging buffers: the (multi-threaded) host copy of chunk
+    i+1 overlaps the DMA of chunk i, instead of cudaMemcpy's serial bounce of the whole 0.5-4 GB array (the
+    reference hands genomepredict a pageable numpy array, orca_predict.py:334)."""
+    device = torch.device(device)
+    key = str(device)
+    if key not in _STAGING:
+        _STAGING[key] = ([torch.empty(_STAGE_BYTES // 4, dtype=torch.float32).pin_memory() for _ in range(2)],
+                         [torch.cuda.Event() for _ in range(2)], torch.cuda.Stream(device=device))
+    bufs, events, cs = _STAGING[key]
+    out = torch.empty(t.shape, dtype=torch.float32, device=device)
+    src, dst = t.view(-1), out.view(-1)
+    n, step = src.numel(), _STAGE_BYTES // 4
+    main = torch.cuda.current_stream(device)
+    cs.wait_stream(main)
+    for i, lo in enumerate(range(0, n, step)):
+        hi = min(lo + step, n)
+        b = i & 1
+        if i >= 2:
+            events[b].synchronize()  # the DMA that last read this staging buffer has finished
+        bufs[b][:hi - lo].copy_(src[lo:hi])
+        with torch.cuda.stream(cs):
+            dst[lo:hi].copy_(bufs[b][:hi - lo], non_blocking=True)
+            events[b].record(cs)
+    main.wait_stream(cs)
+    out.record_stream(main)
+    return out
 
 
 def _log_normmat(model, level, device):
+    """log(normmats[level]) on the device (orca_predict.py:349-353 recomputes and re-uploads it on every eval_step).
+    Cached per (level, device) and re-validated against the SOURCE array on every call -- same object and same
+    checksum -- so that replacing or editing `model.normmats[level]` takes effect as it does in the reference."""
     cache = model.__dict__.setdefault("_distenc_cache", {})
     key = (level, str(device))
-    if key not in cache:
-        nm = model.normmats[level]
-        nm = nm[(None,) * (4 - nm.ndim)]  # orca_predict.py:350
-        cache[key] = torch.log(torch.as_tensor(nm, dtype=torch.float32).to(device))
+    src = model.normmats[level]
+    stamp = float(np.sum(src))
+    hit = cache.get(key)
+    if hit is None or hit[0] is not src or hit[1] != stamp:
+        nm = src[(None,) * (4 - src.ndim)]  # orca_predict.py:350
+        t = torch.log(torch.as_tensor(nm, dtype=torch.float32).to(device))
         # the cached tensor is shared by cascades running on different streams (run_concurrent): make sure it is
         # complete before any other stream can pick it up (one-time cost per model and level)
         if torch.device(device).type == "cuda":
             torch.cuda.current_stream(device).synchronize()
-    return cache[key]
+        cache[key] = hit = (src, stamp, t)
+    return hit[2]
 
 
 _SIDE_STREAMS = {}
@@ -77,23 +118,17 @@ def run_concurrent(jobs, device):
     """Run independent GPU jobs (callables returning tensors) on separate CUDA streams and join them on the
     current stream.  The decoder cascades of different (model, strand) pairs are independent chains of ~20 us
     kernels; interleaving two chains hides each launch's prologue/tail latency behind the other's work."""
-    if len(jobs) <= 1:
+    if len(jobs) <= 1 or torch.device(device).type != "cuda":
         return [job() for job in jobs]
     main = torch.cuda.current_stream(device)
     pool = _SIDE_STREAMS.setdefault(str(device), [])
     while len(pool) < len(jobs):
         pool.append(torch.cuda.Stream(device=device))
     results = []
-    # one launch per conv while interleaving: the single-kernel decoder program is a cooperative launch that
-    # owns every SM, so two of them would serialise
-    prev = _lib.lib().orca_b200_set_decoder_program(0)
-    try:
-        for job, st in zip(jobs, pool):
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                results.append(job())
-    finally:
-        _lib.lib().orca_b200_set_decoder_program(prev)
+    for job, st in zip(jobs, pool):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            results.append(job())
     for st in pool[:len(jobs)]:
         main.wait_stream(st)
 
@@ -120,13 +155,7 @@ def cascade_starts_32mb(mpos, wpos, reverse):
     """Start bins of the six zoom levels: host integer arithmetic only (orca_predict.py:470-499)."""
     starts = [0]
     for j, level in enumerate([32, 16, 8, 4, 2, 1]):
-        if not reverse:
-            si = int(np.clip(np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + starts[j] * 4000))
-                                      / (4000 * level)), 0, 125))
-        else:
-            si = int(np.clip(np.ceil(((wpos + 16000000 - starts[j] * 4000) - (mpos + level * 1000000 / 4))
-                                     / (4000 * level)), 0, 125))
-        starts.append(starts[j] + si * level)
+        starts.append(starts[j] + _next_index_32mb(level, starts[j], mpos, wpos, reverse) * level)
     return starts[:-1]
 
 
@@ -151,19 +180,14 @@ def cascade_32mb(model, encodings, batch, mpos, wpos, reverse, inline_1m=True):
         pred = model.denets[level].forward(xl, distenc, coarse)
         if level == 1 and j > 0 and hasattr(model, "denet_1_pt") and inline_1m:
             pred = pred + model.denet_1_pt.forward(xl)
-        if not reverse:
-            start_index = int(np.clip(np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + starts[j] * 4000))
-                                               / (4000 * level)), 0, 125))
-        else:
-            start_index = int(np.clip(np.ceil(((wpos + 16000000 - starts[j] * 4000) - (mpos + level * 1000000 / 4))
-                                              / (4000 * level)), 0, 125))
+        start_index = _next_index_32mb(level, starts[j], mpos, wpos, reverse)
         starts.append(starts[j] + start_index * level)
         preds.append(pred)
     return preds, starts[:-1]
 
 
 def _next_index_32mb(level, start, mpos, wpos, reverse):
-    """Crop index of the next zoom level (orca_predict.py:470-497)."""
+    """Crop index of the next zoom level (orca_predict.py:470-497) -- the ONE statement of this formula."""
     if not reverse:
         v = np.floor(((mpos - level * 1000000 / 4) - (wpos - 16000000 + start * 4000)) / (4000 * level))
     else:
@@ -171,20 +195,35 @@ def _next_index_32mb(level, start, mpos, wpos, reverse):
     return int(np.clip(v, 0, 125))
 
 
+def _next_index_256mb(level, start, chrlen, mpos, wpos, reverse):
+    """Crop index of the next zoom level of the 256 Mb cascade (orca_predict.py:813-835): `chrlen` clipping, and the
+    mirrored index 250 - (i + 125) on the reverse strand."""
+    if not reverse:
+        proposed = (mpos - level * 1000000 / 4) - (wpos - 128000000 + start * 4000 * 8)
+    else:
+        proposed = (mpos - level * 1000000 / 4) - (wpos + 128000000 - start * 4000 * 8 - level * 1000000)
+    if chrlen is not None:
+        bounds = [0 - (wpos - 128000000), chrlen - level * 1000000 / 2 - (wpos - 128000000)]
+        proposed = np.clip(proposed, bounds[0], bounds[1]) if bounds[0] < bounds[1] else bounds[0]
+    i = int(np.clip(np.floor(proposed / (4000 * level)), 0, 125))
+    return 250 - (i + 125) if reverse else i
+
+
 def cascade_32mb_lanes(model, lanes, mpos, wpos, inline_1m=True):
     """Several independent cascades of ONE model (e.g. its two strands) as one batched chain: every decoder call
     carries one batch element per lane, so the 118 dependent layers of a level are paid once instead of per strand
     (each lane keeps its own crop windows; the arithmetic per lane is exactly cascade_32mb's).
 
-    lanes: [(encodings {level: (1, 128, P/level)}, reverse), ...].  Returns (preds: list over levels of
-    (n_lanes, C, 250, 250), starts: per-lane start bins)."""
+    lanes: [(encodings {level: (B, 128, P/level)}, reverse), ...].  Returns (preds: list over levels of
+    (n_lanes * B, C, 250, 250), lane-major; starts: per-lane start bins)."""
     n = len(lanes)
     device = lanes[0][0][1].device
+    B = lanes[0][0][1].shape[0]
     starts, sidx, preds = [[0] for _ in lanes], [0] * n, []
     for j, level in enumerate([32, 16, 8, 4, 2, 1]):
-        distenc = _log_normmat(model, level, device).expand(n, -1, -1, -1)
+        distenc = _log_normmat(model, level, device).expand(n * B, -1, -1, -1)
         xl = torch.cat([enc[level][:, :, int(st[j] / level):int(st[j] / level) + 250] for (enc, _), st in zip(lanes, starts)], 0)
-        coarse = None if j == 0 else torch.stack([preds[j - 1][i, :, si:si + 125, si:si + 125] for i, si in enumerate(sidx)], 0)
+        coarse = None if j == 0 else torch.cat([preds[j - 1][i * B:(i + 1) * B, :, si:si + 125, si:si + 125] for i, si in enumerate(sidx)], 0)
         pred = model.denets[level].forward(xl, distenc, coarse)
         if level == 1 and hasattr(model, "denet_1_pt") and inline_1m:
             pred = pred + model.denet_1_pt.forward(xl)
@@ -215,23 +254,29 @@ def genomepredict(sequence, mchr, mpos=-1, wpos=-1, models=(), targets=None, ann
     if not models or not all(isinstance(m, torch.nn.Module) for m in models):
         raise ValueError("models must be a non-empty list of shell modules")
     device = _device_of(models[0])
-    with torch.no_grad(), torch.cuda.device(device):
+    with torch.cuda.device(device):
+        return _genomepredict_on(device, sequence, mchr, mpos, wpos, models)
+
+
+def _strand_lanes_32mb(model, seq_dev, mpos, wpos):
+    """One model, both strands: two encoder passes over the one uploaded tensor, ONE U-net call and ONE decoder
+    chain at batch 2B (the strands are the lanes).  Returns (per-level strand-averaged maps, forward-strand starts)."""
+    B = seq_dev.shape[0]
+    enc = torch.cat([encode_strand(model, seq_dev, False), encode_strand(model, seq_dev, True)], 0)
+    outs = model.net(enc)
+    lanes = [({lvl: t[i * B:(i + 1) * B] for lvl, t in zip([1, 2, 4, 8, 16, 32], outs)}, rev) for i, rev in enumerate((False, True))]
+    preds, starts = cascade_32mb_lanes(model, lanes, mpos, wpos)
+    return _average_strands([p[:B] for p in preds], [p[B:] for p in preds]), starts[0]
+
+
+def _genomepredict_on(device, sequence, mchr, mpos, wpos, models):
+    """Body of genomepredict for shells living on `device` (the host logic is device-agnostic: tests/test_host.py
+    drives it on the CPU with stand-in networks against fixtures from the unmodified reference driver)."""
+    with torch.no_grad():
         seq_dev = _to_device_sequence(sequence, device)
-        B = seq_dev.shape[0]
-        # encoders saturate the GPU on their own: run them back to back; the (model, strand) cascades are
-        # independent latency-bound chains: run them concurrently
-        passes = [(reverse, model) for reverse in (False, True) for model in models]
-        enc4k = [encode_strand(model, seq_dev, reverse) for reverse, model in passes]
-
-        def cascade(reverse, model, e):
-            encs = dict(zip([1, 2, 4, 8, 16, 32], model.net(e)))
-            return cascade_32mb(model, encs, B, mpos, wpos, reverse)
-
-        results = run_concurrent([lambda r=r, m=m, e=e: cascade(r, m, e) for (r, m), e in zip(passes, enc4k)], device)
-        per_strand = [preds for preds, _ in results]
+        results = [_strand_lanes_32mb(model, seq_dev, mpos, wpos) for model in models]
+        stacked = [torch.stack(avg) for avg, _ in results]
         starts0 = results[0][1]
-        n = len(models)
-        stacked = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])) for i in range(n)]
         host = [s.cpu().numpy() for s in stacked]
     output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
     output["start_coords"] = [wpos - 16000000 + s * 4000 for s in starts0]
@@ -284,40 +329,32 @@ def prepare_background(normmat, device):
     return t
 
 
-def background_level(normmat_dev, r0, f, flip=False, size=250):
-    """log(block-nanmean) of an (n, n) float64 device matrix -> (1, 1, size, size) float32."""
+def background_level(normmat_dev, r0, f, flip=False, size=250, with_mean=False):
+    """log(block-nanmean) of an (n, n) float64 device matrix -> (1, 1, size, size) float32 (flipped if `flip`);
+    with_mean=True also returns the float64 block mean itself, (1, size, size), never flipped (orca_predict.py:724-737)."""
     out = torch.empty((1, 1, size, size), dtype=torch.float32, device=normmat_dev.device)
+    mean = torch.empty((1, size, size), dtype=torch.float64, device=normmat_dev.device) if with_mean else None
     with torch.cuda.device(normmat_dev.device):
-        _lib.check(_lib.lib().orca_b200_background_forward(
+        _lib.check(_lib.lib().orca_b200_background_level(
             normmat_dev.data_ptr(), normmat_dev.shape[0], int(r0), int(f), size, 1 if flip else 0, out.data_ptr(),
-            torch.cuda.current_stream(normmat_dev.device).cuda_stream))
-    return out
+            mean.data_ptr() if with_mean else None, torch.cuda.current_stream(normmat_dev.device).cuda_stream))
+    return (out, mean) if with_mean else out
 
 
 def cascade_256mb(model, encodings, batch, normmat_dev, chrlen, mpos, wpos, reverse):
     """Decoder cascade 256 -> 32 Mb of one (model, strand) (orca_predict.py:692-836).
-    Returns (preds, starts, per-level background matrices as float32 device tensors (un-logged))."""
+    Returns (preds, starts, per-level float64 block-mean background matrices (1, 250, 250), device tensors)."""
     preds, starts, ns = [], [0], {}
     start_index = 0
     for j, level in enumerate([256, 128, 64, 32]):
         f = level // 8
-        logbg = background_level(normmat_dev, starts[j], f, flip=False)
-        ns[level] = logbg
-        distenc = (torch.flip(logbg, [2, 3]) if reverse else logbg).expand(batch, -1, -1, -1)
+        logbg, ns[level] = background_level(normmat_dev, starts[j], f, flip=reverse, with_mean=True)
+        distenc = logbg.expand(batch, -1, -1, -1)
         s = int(starts[j] / f)
         xl = encodings[level][:, :, s:s + 250]
         coarse = None if j == 0 else preds[j - 1][:, :, start_index:start_index + 125, start_index:start_index + 125]
         pred = model.denets[level].forward(xl, distenc, coarse)
-        if not reverse:
-            proposed = (mpos - level * 1000000 / 4) - (wpos - 128000000 + starts[j] * 4000 * 8)
-        else:
-            proposed = (mpos - level * 1000000 / 4) - (wpos + 128000000 - starts[j] * 4000 * 8 - level * 1000000)
-        if chrlen is not None:
-            bounds = [0 - (wpos - 128000000), chrlen - level * 1000000 / 2 - (wpos - 128000000)]
-            proposed = np.clip(proposed, bounds[0], bounds[1]) if bounds[0] < bounds[1] else bounds[0]
-        start_index = int(np.clip(np.floor(proposed / (4000 * level)), 0, 125))
-        if reverse:
-            start_index = 250 - (start_index + 125)
+        start_index = _next_index_256mb(level, starts[j], chrlen, mpos, wpos, reverse)
         starts.append(starts[j] + start_index * level // 8)
         preds.append(pred)
     return preds, starts[:-1], ns
@@ -338,15 +375,7 @@ def cascade_256mb_lanes(model, lanes, normmat_dev, chrlen, mpos, wpos):
         coarse = None if j == 0 else torch.stack([preds[j - 1][i, :, si:si + 125, si:si + 125] for i, si in enumerate(sidx)], 0)
         pred = model.denets[level].forward(torch.cat(xs, 0), torch.stack(dist, 0), coarse)
         for i, (_, rev) in enumerate(lanes):
-            if not rev:
-                proposed = (mpos - level * 1000000 / 4) - (wpos - 128000000 + starts[i][j] * 4000 * 8)
-            else:
-                proposed = (mpos - level * 1000000 / 4) - (wpos + 128000000 - starts[i][j] * 4000 * 8 - level * 1000000)
-            if chrlen is not None:
-                bounds = [0 - (wpos - 128000000), chrlen - level * 1000000 / 2 - (wpos - 128000000)]
-                proposed = np.clip(proposed, bounds[0], bounds[1]) if bounds[0] < bounds[1] else bounds[0]
-            si = int(np.clip(np.floor(proposed / (4000 * level)), 0, 125))
-            sidx[i] = 250 - (si + 125) if rev else si
+            sidx[i] = _next_index_256mb(level, starts[i][j], chrlen, mpos, wpos, rev)
             starts[i].append(starts[i][j] + sidx[i] * level // 8)
         preds.append(pred)
     return preds, [st[:-1] for st in starts]
@@ -361,7 +390,12 @@ def genomepredict_256Mb(sequence, mchr, normmats, chrlen, mpos=-1, wpos=-1, mode
         raise RuntimeError("orca_b200 has no CPU path")
     models = list(models)
     device = _device_of(models[0])
-    with torch.no_grad(), torch.cuda.device(device):
+    with torch.cuda.device(device):
+        return _genomepredict_256mb_on(device, sequence, mchr, normmats, chrlen, mpos, wpos, models, padding_chr)
+
+
+def _genomepredict_256mb_on(device, sequence, mchr, normmats, chrlen, mpos, wpos, models, padding_chr=None):
+    with torch.no_grad():
         seq_dev = _to_device_sequence(sequence, device)
         B = seq_dev.shape[0]
         nm_dev = [prepare_background(nm, device) for nm in normmats]
@@ -378,7 +412,7 @@ def genomepredict_256Mb(sequence, mchr, normmats, chrlen, mpos=-1, wpos=-1, mode
                     starts0 = starts
         n = len(models)
         host = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])).cpu().numpy() for i in range(n)]
-        ns_host = [{lvl: torch.exp(t[0]).cpu().numpy().astype(np.float64) for lvl, t in ns.items()} for ns in allns]
+        ns_host = [{lvl: t.cpu().numpy() for lvl, t in ns.items()} for ns in allns]
     output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
     output["start_coords"] = [wpos - 128000000 + s * 32000 for s in starts0]
     output["end_coords"] = [np.fmin(int(output["start_coords"][ii] + 256000000 / 2 ** ii), chrlen) for ii in range(4)]

@@ -10,8 +10,12 @@ import numpy as np
 import torch
 
 
-def fill_state_dict(shapes, seed):
+def fill_state_dict(shapes, seed, recipe="default"):
     """Return {key: tensor} for an ordered mapping key -> shape/dtype template.
+
+    recipe: "default" (below); "wide_bn" = BatchNorm folded scale gamma/sqrt(var) log-uniform in [0.1, 10] per
+    channel (trained checkpoints can carry such scales; they stress the fp16 range of the single-pass encoder
+    stages); "heavy_tail" = conv weights from a Student-t (3 d.o.f.) instead of a uniform distribution.
 
     `shapes` is any ordered mapping whose values have `.shape` and `.dtype`
     (e.g. `module.state_dict()`).  Recipe: conv weight/bias
@@ -35,6 +39,8 @@ def fill_state_dict(shapes, seed):
         if prefix in bn_prefixes:
             if leaf == "weight":
                 v = rng.uniform(0.5, 1.5, size=shape)
+                if recipe == "wide_bn":
+                    v = np.exp(rng.uniform(np.log(0.1), np.log(10.0), size=shape))  # x 1/sqrt(var ~ U(0.5,1.5)) below
             elif leaf == "bias":
                 v = rng.normal(0.0, 0.1, size=shape)
             elif leaf == "running_mean":
@@ -52,6 +58,8 @@ def fill_state_dict(shapes, seed):
             else:
                 raise KeyError(k)
             v = rng.uniform(-bound, bound, size=shape)
+            if recipe == "heavy_tail" and leaf == "weight":
+                v = rng.standard_t(3, size=shape) * bound / np.sqrt(3.0)  # same variance as U(-bound, bound) x 3 d.o.f. tail
         out[k] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
     return out
 
@@ -74,6 +82,28 @@ def random_sequence(batch, length, seed, n_fraction=0.0):
     if n_fraction > 0:
         mask = rng.random((batch, length)) < n_fraction
         seq[mask] = 0.25
+    return seq
+
+
+def hard_sequence(batch, length, seed, kind):
+    """Inputs that stress the encoder's early stages: "alln" (every base unknown: 0.25 x 4, selene_utils2.py:216-230),
+    "homopolymer" (poly-A with a poly-T block), "nruns" (random bases with 10 % of the positions inside long N runs),
+    "random"."""
+    rng = np.random.default_rng(seed)
+    seq = random_sequence(batch, length, seed)
+    if kind == "alln":
+        seq[:] = 0.25
+    elif kind == "homopolymer":
+        seq[:] = 0.0
+        seq[:, :, 0] = 1.0
+        seq[:, length // 3: length // 2] = [0.0, 0.0, 0.0, 1.0]
+    elif kind == "nruns":
+        n_runs = max(1, length // 20000)
+        for b in range(batch):
+            for s0 in rng.integers(0, length - 2000, size=n_runs):
+                seq[b, s0:s0 + 2000] = 0.25
+    elif kind != "random":
+        raise ValueError(kind)
     return seq
 
 

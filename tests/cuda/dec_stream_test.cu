@@ -1,0 +1,382 @@
+// Standalone harness for the decoder stream kernel (orca_b200/csrc/conv2d_stream.cu + dec_glue.cu), no Python:
+//   1. single layers of every variant (64->32, 32->64 + residual + ReLU, 64->64 + residual, 128->64 as two K halves) for
+//      dilations incl. d > S, against a double-precision CPU convolution on small maps;
+//   2. a multi-layer residual program (all dilations, 64->64 layers in between) at S = 250, batch 2, run FUSED (one
+//      launch: row flags, buffer recycling, shared-memory re-carving) against the same layers run ONE LAUNCH EACH --
+//      the arithmetic per tile is schedule independent, so the two must agree bit for bit;
+//   3. timing of a Decoder-shaped 116-layer program at batch 1 and 2 (CUDA events).
+// Build: see tests/cuda/build_dec_stream_test.sh.   Run: ./dec_stream_test [quick]
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../orca_b200/csrc/common.h"
+#include "../../orca_b200/csrc/dec_stream.h"
+
+namespace orca {
+static std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+std::atomic<uint64_t> g_launches{0};
+bool final_head_ok(const ConvLayer&, const ConvLayer&) { return true; }
+}  // namespace orca
+using namespace orca;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d: %s\n", #x, __LINE__, cudaGetErrorString(e_)); exit(2); } } while (0)
+#define OK(x) do { int s_ = (x); if (s_ != 0) { printf("orca error %d at line %d: %s\n", s_, __LINE__, g_err.c_str()); exit(3); } } while (0)
+
+struct HostLayer {
+  ConvLayer L;
+  std::vector<float> w, b;  // [tap][c_in][c_out], [c_out]
+};
+static std::vector<void*> g_allocs;
+
+static HostLayer make_layer(int c_in, int c_out, int d, std::mt19937& rng) {
+  HostLayer h;
+  h.L.c_in = c_in; h.L.c_out = c_out; h.L.kh = 3; h.L.kw = 3; h.L.dil = d;
+  const float bound = 1.0f / std::sqrt((float)(9 * c_in));
+  std::uniform_real_distribution<float> u(-bound, bound);
+  h.w.resize((size_t)9 * c_in * c_out);
+  h.b.resize(c_out);
+  for (auto& v : h.w) v = u(rng);
+  for (auto& v : h.b) v = u(rng);
+  OK(ds_pack_layer(h.L, h.w.data(), g_allocs));
+  CK(cudaMalloc(&h.L.b, c_out * 4));
+  CK(cudaMemcpy(h.L.b, h.b.data(), c_out * 4, cudaMemcpyHostToDevice));
+  return h;
+}
+
+static DMap alloc_map(int nb, int C, int S) {
+  void* p;
+  CK(cudaMalloc(&p, dmap_bytes(nb, C, S)));
+  CK(cudaMemset(p, 0xFF, dmap_bytes(nb, C, S)));  // NaN pattern: unwritten pixels show up
+  return dmap_make(p, nb, C, S);
+}
+static DMap upload_map(const std::vector<float>& x, int nb, int C, int S) {
+  DMap m = alloc_map(nb, C, S);
+  float* d;
+  CK(cudaMalloc(&d, x.size() * 4));
+  CK(cudaMemcpy(d, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+  OK(ds_from_f32(d, &m, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaFree(d));
+  return m;
+}
+static std::vector<float> download_map(const DMap& m) {
+  std::vector<float> x((size_t)m.nb * m.S * m.S * m.C);
+  float* d;
+  CK(cudaMalloc(&d, x.size() * 4));
+  OK(ds_to_f32(m, d, 0));
+  CK(cudaMemcpy(x.data(), d, x.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+  return x;
+}
+static std::vector<float> random_map(int nb, int C, int S, std::mt19937& rng) {
+  std::vector<float> x((size_t)nb * S * S * C);
+  std::normal_distribution<float> n(0.f, 1.f);
+  for (auto& v : x) v = n(rng);
+  return x;
+}
+
+// CPU reference (double): channel-last [nb][S][S][C]; k0 = first input channel used, kin = number of input channels
+static std::vector<float> cpu_conv(const std::vector<float>& in, int Cin_total, int k0, const HostLayer& h, int wk0, int kin, bool use_bias,
+                                   const std::vector<float>* res, int relu, int nb, int S) {
+  const int co = h.L.c_out, d = h.L.dil, cin_w = h.L.c_in;
+  std::vector<float> out((size_t)nb * S * S * co);
+#pragma omp parallel for collapse(2)
+  for (int b = 0; b < nb; ++b)
+    for (int y = 0; y < S; ++y)
+      for (int x = 0; x < S; ++x) {
+        std::vector<double> acc(co, 0.0);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int yy = y + (tap / 3 - 1) * d, xx = x + (tap % 3 - 1) * d;
+          if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
+          const float* ip = &in[(((size_t)b * S + yy) * S + xx) * Cin_total + k0];
+          for (int ci = 0; ci < kin; ++ci) {
+            const double v = ip[ci];
+            const float* wp = &h.w[((size_t)tap * cin_w + wk0 + ci) * co];
+            for (int n = 0; n < co; ++n) acc[n] += v * wp[n];
+          }
+        }
+        float* op = &out[(((size_t)b * S + y) * S + x) * co];
+        for (int n = 0; n < co; ++n) {
+          double t = acc[n] + (use_bias ? h.b[n] : 0.0);
+          if (relu) t = t > 0 ? t : 0;
+          if (res) t += (*res)[(((size_t)b * S + y) * S + x) * co + n];
+          op[n] = (float)t;
+        }
+      }
+  return out;
+}
+
+static double relerr(const std::vector<float>& a, const std::vector<float>& b, bool* finite) {
+  double me = 0, mr = 0;
+  *finite = true;
+  for (size_t i = 0; i < a.size(); ++i) {
+    if (!std::isfinite(a[i])) *finite = false;
+    me = std::fmax(me, std::fabs((double)a[i] - b[i]));
+    mr = std::fmax(mr, std::fabs((double)b[i]));
+  }
+  return me / (mr > 0 ? mr : 1);
+}
+
+static void* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+static void ensure_scratch(int layers, int nb, int S) {
+  const size_t need = DecStream::scratch_bytes(layers, nb, S);
+  if (need > g_scratch_bytes) {
+    if (g_scratch) CK(cudaFree(g_scratch));
+    CK(cudaMalloc(&g_scratch, need));
+    g_scratch_bytes = need;
+  }
+}
+
+static int n_fail = 0;
+static void check_stall(const char* what) {
+  unsigned int dbg[184];
+  OK(ds_debug_read(dbg));
+  if (dbg[0]) {
+    printf("STALL in %s; stuck waits as line/layer x count (a block):", what);
+    for (unsigned i = 0; i < 60 && dbg[4 + 3 * i]; ++i) printf(" %u/L%u x%u (b%u)", dbg[4 + 3 * i] >> 8, dbg[4 + 3 * i] & 255, dbg[5 + 3 * i], dbg[6 + 3 * i]);
+    printf("\n");
+    ++n_fail;
+    OK(ds_debug_enable(1));  // re-arm
+  }
+}
+static void report(const char* what, double err, bool finite, double tol) {
+  const bool ok = finite && err <= tol;
+  printf("%-64s relerr %.2e %s\n", what, err, ok ? "PASS" : "FAIL");
+  if (!ok) ++n_fail;
+}
+
+static void single_layer_tests() {
+  std::mt19937 rng(1234);
+  const int nb = 2;
+  for (int S : {40, 130}) {
+    for (int d : {1, 2, 4, 8, 16, 32, 64}) {
+      ensure_scratch(4, nb, S);
+      char name[128];
+      {  // 64 -> 32, no residual, ReLU
+        HostLayer h = make_layer(64, 32, d, rng);
+        auto x = random_map(nb, 64, S, rng);
+        DMap in = upload_map(x, nb, 64, S), out = alloc_map(nb, 32, S);
+        DecStream p;
+        OK(p.add(h.L, -1, 1, in, nullptr, &out, 1));
+        OK(p.run(g_scratch, g_scratch_bytes, 0));
+        CK(cudaDeviceSynchronize());
+        auto ref = cpu_conv(x, 64, 0, h, 0, 64, true, nullptr, 1, nb, S);
+        bool fin;
+        const double e = relerr(download_map(out), ref, &fin);
+        snprintf(name, sizeof name, "64->32 relu            S=%d d=%d", S, d);
+        report(name, e, fin, 5e-5);
+        CK(cudaFree(in.p)); CK(cudaFree(out.p));
+      }
+      {  // 32 -> 64 + residual + ReLU
+        HostLayer h = make_layer(32, 64, d, rng);
+        auto x = random_map(nb, 32, S, rng), r = random_map(nb, 64, S, rng);
+        DMap in = upload_map(x, nb, 32, S), res = upload_map(r, nb, 64, S), out = alloc_map(nb, 64, S);
+        DecStream p;
+        OK(p.add(h.L, -1, 1, in, &res, &out, 1));
+        OK(p.run(g_scratch, g_scratch_bytes, 0));
+        CK(cudaDeviceSynchronize());
+        auto ref = cpu_conv(x, 32, 0, h, 0, 32, true, &r, 1, nb, S);
+        bool fin;
+        const double e = relerr(download_map(out), ref, &fin);
+        snprintf(name, sizeof name, "32->64 relu + residual S=%d d=%d", S, d);
+        report(name, e, fin, 5e-5);
+        CK(cudaFree(in.p)); CK(cudaFree(res.p)); CK(cudaFree(out.p));
+      }
+    }
+    {  // 64 -> 64 + residual, d = 1
+      HostLayer h = make_layer(64, 64, 1, rng);
+      auto x = random_map(nb, 64, S, rng), r = random_map(nb, 64, S, rng);
+      DMap in = upload_map(x, nb, 64, S), res = upload_map(r, nb, 64, S), out = alloc_map(nb, 64, S);
+      DecStream p;
+      OK(p.add(h.L, -1, 1, in, &res, &out, 0));
+      OK(p.run(g_scratch, g_scratch_bytes, 0));
+      CK(cudaDeviceSynchronize());
+      auto ref = cpu_conv(x, 64, 0, h, 0, 64, true, &r, 0, nb, S);
+      bool fin;
+      const double e = relerr(download_map(out), ref, &fin);
+      char name[128];
+      snprintf(name, sizeof name, "64->64 + residual      S=%d d=1", S);
+      report(name, e, fin, 5e-5);
+      CK(cudaFree(in.p)); CK(cudaFree(res.p)); CK(cudaFree(out.p));
+    }
+    {  // 128 -> 64 as two K halves chained through the residual, then 128 -> 32
+      for (int co : {64, 32}) {
+        HostLayer h = make_layer(128, co, 1, rng);
+        auto x = random_map(nb, 128, S, rng), r = random_map(nb, co, S, rng);
+        DMap in = upload_map(x, nb, 128, S), res = upload_map(r, nb, co, S), mid = alloc_map(nb, co, S), out = alloc_map(nb, co, S);
+        DecStream p;
+        OK(p.add(h.L, 0, 0, in, &res, &mid, 0));
+        OK(p.add(h.L, 1, 1, in, &mid, &out, 0));
+        OK(p.run(g_scratch, g_scratch_bytes, 0));
+        CK(cudaDeviceSynchronize());
+        auto m = cpu_conv(x, 128, 0, h, 0, 64, false, &r, 0, nb, S);
+        auto ref = cpu_conv(x, 128, 64, h, 64, 64, true, &m, 0, nb, S);
+        bool fin;
+        const double e = relerr(download_map(out), ref, &fin);
+        char name[128];
+        snprintf(name, sizeof name, "128->%d (two K halves) + residual S=%d d=1", co, S);
+        report(name, e, fin, 5e-5);
+        CK(cudaFree(in.p)); CK(cudaFree(res.p)); CK(cudaFree(mid.p)); CK(cudaFree(out.p));
+      }
+    }
+  }
+}
+
+// Decoder-shaped program: [two combiner-like 64->64 pairs] then residual bottleneck units over `dils`.
+// Buffers: 0..2 = X (64 ch), 3..4 = T (32 ch), 5 = the input map (never written).
+struct Program {
+  std::vector<HostLayer> layers;
+  std::vector<int> in_i, res_i, out_i, relu;
+};
+static int pick_x(int e0, int e1) {
+  for (int i = 0; i < 3; ++i)
+    if (i != e0 && i != e1) return i;
+  return -1;
+}
+static Program build_program(const std::vector<int>& dils, bool combiners, std::mt19937& rng) {
+  Program P;
+  auto push = [&](int ci, int co, int d, int in, int res, int out, int relu) {
+    P.layers.push_back(make_layer(ci, co, d, rng));
+    P.in_i.push_back(in); P.res_i.push_back(res); P.out_i.push_back(out); P.relu.push_back(relu);
+  };
+  int cur = 5;
+  if (combiners) {
+    for (int i = 0; i < 2; ++i) {  // a1 = conv(conv(cur)) ; cur = relu(conv(relu(conv(a1)))) + a1
+      const int t0 = pick_x(cur, -1);
+      push(64, 64, 1, cur, -1, t0, 0);
+      const int a1 = pick_x(cur, t0);
+      push(64, 64, 1, t0, -1, a1, 0);
+      const int a2 = pick_x(a1, -1);
+      push(64, 64, 1, a1, -1, a2, 1);
+      const int a3 = pick_x(a1, a2);
+      push(64, 64, 1, a2, a1, a3, 1);
+      cur = a3;
+    }
+  }
+  int tn = 3;
+  for (int d : dils) {
+    for (int half = 0; half < 2; ++half) {  // lm (linear) then m (ReLU), both with the residual
+      const int t = tn; tn = tn == 3 ? 4 : 3;
+      push(64, 32, d, cur, -1, t, half);
+      const int o = pick_x(cur, -1);
+      push(32, 64, d, t, cur, o, half);
+      cur = o;
+    }
+  }
+  return P;
+}
+
+static float run_program(const Program& P, DMap* bufs, bool fused, int reps = 1) {
+  const int n = (int)P.layers.size();
+  ensure_scratch(n + 4, bufs[5].nb, bufs[5].S);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float ms = 0;
+  if (fused) {
+    DecStream p;
+    for (int l = 0; l < n; ++l)
+      OK(p.add(P.layers[l].L, -1, 1, bufs[P.in_i[l]], P.res_i[l] >= 0 ? &bufs[P.res_i[l]] : nullptr, &bufs[P.out_i[l]], P.relu[l]));
+    OK(p.run(g_scratch, g_scratch_bytes, 0));  // warm-up
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) OK(p.run(g_scratch, g_scratch_bytes, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
+    check_stall("fused program");
+  } else {
+    for (int l = 0; l < n; ++l) {
+      DecStream p;
+      OK(p.add(P.layers[l].L, -1, 1, bufs[P.in_i[l]], P.res_i[l] >= 0 ? &bufs[P.res_i[l]] : nullptr, &bufs[P.out_i[l]], P.relu[l]));
+      OK(p.run(g_scratch, g_scratch_bytes, 0));
+      const cudaError_t e = cudaDeviceSynchronize();
+      char what[128];
+      snprintf(what, sizeof what, "layer %d (%d->%d d=%d res=%d) alone", l, P.layers[l].L.c_in, P.layers[l].L.c_out, P.layers[l].L.dil, P.res_i[l]);
+      if (e != cudaSuccess) { printf("CUDA error in %s: %s\n", what, cudaGetErrorString(e)); exit(2); }
+      check_stall(what);
+    }
+  }
+  return ms;
+}
+
+static void fused_vs_layerwise(int nb, int S) {
+  std::mt19937 rng(99);
+  Program P = build_program({1, 2, 4, 8, 16, 32, 64, 1, 64, 2}, true, rng);
+  auto x = random_map(nb, 64, S, rng);
+  DMap bufs[6];
+  for (int i = 0; i < 3; ++i) bufs[i] = alloc_map(nb, 64, S);
+  for (int i = 3; i < 5; ++i) bufs[i] = alloc_map(nb, 32, S);
+  bufs[5] = upload_map(x, nb, 64, S);
+  const int last = P.out_i.back();
+  run_program(P, bufs, false);
+  std::vector<uint8_t> a(dmap_bytes(nb, 64, S)), b(a.size());
+  CK(cudaMemcpy(a.data(), bufs[last].p, a.size(), cudaMemcpyDeviceToHost));
+  auto va = download_map(bufs[last]);
+  for (int i = 0; i < 5; ++i) CK(cudaMemset(bufs[i].p, 0xFF, dmap_bytes(nb, bufs[i].C, S)));
+  for (int rep = 0; rep < 1; ++rep) {
+    run_program(P, bufs, true);
+    CK(cudaMemcpy(b.data(), bufs[last].p, b.size(), cudaMemcpyDeviceToHost));
+    size_t diff = 0;
+    for (size_t i = 0; i < a.size(); ++i) diff += a[i] != b[i];
+    bool fin = true;
+    double amax = 0;
+    for (float v : va) { if (!std::isfinite(v)) fin = false; amax = std::fmax(amax, std::fabs(v)); }
+    char name[128];
+    snprintf(name, sizeof name, "fused %zu-layer program == one launch per layer  nb=%d S=%d (|out| %.3g)", P.layers.size(), nb, S, amax);
+    printf("%-64s %zu differing bytes %s\n", name, diff, (diff == 0 && fin) ? "PASS" : "FAIL");
+    if (diff != 0 || !fin) ++n_fail;
+  }
+  for (auto& m : bufs) CK(cudaFree(m.p));
+}
+
+static void timing(int nb) {
+  std::mt19937 rng(7);
+  std::vector<int> dils;
+  const int base[7] = {1, 2, 4, 8, 16, 32, 64};
+  for (int r = 0; r < 4; ++r) for (int i = 0; i < 7; ++i) dils.push_back(base[i]);
+  dils.erase(dils.begin());  // 27 units after the combiner stage (Decoder.forward with a coarse input)
+  Program P = build_program(dils, true, rng);
+  const int S = 250;
+  auto x = random_map(nb, 64, S, rng);
+  DMap bufs[6];
+  for (int i = 0; i < 3; ++i) bufs[i] = alloc_map(nb, 64, S);
+  for (int i = 3; i < 5; ++i) bufs[i] = alloc_map(nb, 32, S);
+  bufs[5] = upload_map(x, nb, 64, S);
+  const float ms = run_program(P, bufs, true, 10);
+  double flop = 0;
+  for (auto& h : P.layers) flop += 2.0 * nb * S * S * 9.0 * h.L.c_in * h.L.c_out;
+  printf("timing: %zu-layer Decoder-shaped program, batch %d, S=250: %.3f ms per launch, %.1f algorithmic TFLOP/s (x3 issued: %.1f)\n",
+         P.layers.size(), nb, ms, flop / ms * 1e-9, 3 * flop / ms * 1e-9);
+  for (auto& m : bufs) CK(cudaFree(m.p));
+}
+
+int main(int argc, char** argv) {
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  OK(ds_debug_enable(1));
+  single_layer_tests();
+  check_stall("single-layer tests");
+  fused_vs_layerwise(1, 64);
+  fused_vs_layerwise(2, 250);
+  if (!quick) { timing(1); timing(2); }
+  printf("%s (%d failures)\n", n_fail ? "FAILED" : "ALL PASS", n_fail);
+  return n_fail ? 1 : 0;
+}

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, relerr
 from orca_b200 import _lib, models, modules, parallel, synthetic
 
 
@@ -209,8 +209,10 @@ def test_lane_batched_cascades_equal_separate_cascades(monkeypatch):
 
     # 256 Mb analogue; the device background kernel is replaced by the oracle's numpy restatement
     nm = synthetic.normmat_256mb(chrlen_bins=7000)
-    monkeypatch.setattr(predict, "background_level",
-                        lambda normmat, r0, f, flip=False, size=250: oracle.background_level(normmat, r0, f, size, flip))
+    def fake_level(normmat, r0, f, flip=False, size=250, with_mean=False):
+        log = oracle.background_level(normmat, r0, f, size, flip)
+        return (log, torch.exp(oracle.background_level(normmat, r0, f, size, False)[0].double())) if with_mean else log
+    monkeypatch.setattr(predict, "background_level", fake_level)
     shell.denets = {lvl: _FakeDecoder(1.0 + 0.1 * i) for i, lvl in enumerate([32, 64, 128, 256])}
     encs = [{lvl: torch.from_numpy(rng.standard_normal((1, 128, 8000 * 32 // lvl)).astype(np.float32)) for lvl in [32, 64, 128, 256]}
             for _ in range(2)]
@@ -221,3 +223,58 @@ def test_lane_batched_cascades_equal_separate_cascades(monkeypatch):
         assert st == lanes_s[i]
         for a, b in zip(p, lanes_p):
             assert torch.equal(a[0], b[i])
+
+
+def test_cascade_index_math_matches_reference_drivers(monkeypatch):
+    """Driver logic at the edges (crop index clipped to 0 and 125, mpos = wpos, shifted windows, chromosomes shorter
+    than the window so that bounds[0] >= bounds[1], both strands): orca_b200.predict's host logic on stand-in networks
+    (tests/fakes.py) against maps the UNMODIFIED orca_predict.genomepredict / genomepredict_256Mb produced with the
+    same stand-ins (oracle/make_golden.py `cascade_index_cases`)."""
+    import fakes
+    import orca_oracle as oracle
+    from orca_b200 import predict
+    g = np.load(os.path.join(GOLDEN, "cascade_index_cases.npz"))
+    cpu = torch.device("cpu")
+    sh = fakes.FakeShell("h1esc")
+    seq = fakes.stub_sequence(32_000_000, int(g["seq32_seed"]))
+    for i, (mpos, wpos) in enumerate(fakes.CASES_32MB):
+        out = predict._genomepredict_on(cpu, seq, "chrS", mpos, wpos, [sh])
+        assert out["start_coords"] == [int(v) for v in g["s32_%d" % i]], (mpos, wpos)
+        got = np.stack(out["predictions"][0])[:, ::5, ::5]  # the fixture keeps every 5th row / column
+        assert relerr(got, g["p32_%d" % i]) <= 1e-6, (mpos, wpos)
+    starts = [predict.cascade_starts_32mb(m, w, False) for m, w in fakes.CASES_32MB]
+    assert any(s[-1] == s[-2] for s in starts) and any((s[1] - s[0]) == 125 * 32 for s in starts)  # both clip edges were hit
+
+    def fake_level(normmat, r0, f, flip=False, size=250, with_mean=False):
+        nm = normmat.numpy() if isinstance(normmat, torch.Tensor) else normmat
+        log = oracle.background_level(nm, r0, f, size, flip)
+        blk = nm[r0:r0 + size * f, r0:r0 + size * f]
+        mean = np.nanmean(np.nanmean(np.reshape(blk, (1, size, f, size, f)), axis=4), axis=2)
+        return (log, torch.from_numpy(mean)) if with_mean else log
+    monkeypatch.setattr(predict, "background_level", fake_level)
+    sh = fakes.FakeShell("h1esc_256m")
+    seq = fakes.stub_sequence(64000, int(g["seq256_seed"]))
+    for i, (mpos, wpos, chrlen) in enumerate(fakes.CASES_256MB):
+        nm = synthetic.normmat_256mb(chrlen_bins=min(8000, chrlen // 32000))
+        out = predict._genomepredict_256mb_on(cpu, seq, "chrS", [nm], chrlen, mpos, wpos, [sh])
+        assert out["start_coords"] == [int(v) for v in g["s256_%d" % i]], (mpos, wpos, chrlen)
+        assert [int(v) for v in out["end_coords"]] == [int(v) for v in g["e256_%d" % i]]
+        assert relerr(np.stack(out["predictions"][0])[:, ::5, ::5], g["p256_%d" % i]) <= 1e-6, (mpos, wpos, chrlen)
+        nms = np.stack([np.stack([ns[l][0] for l in (256, 128, 64, 32)]) for ns in out["normmats"]])[:, :, ::10, ::10]
+        assert nms.dtype == np.float64 and np.array_equal(nms, g["n256_%d" % i])
+
+
+def test_log_normmat_cache_follows_the_source_array():
+    """the cached log(normmat) must track replacement and in-place edits of model.normmats[level]."""
+    import fakes
+    from orca_b200 import predict
+    sh = fakes.FakeShell("h1esc")
+    cpu = torch.device("cpu")
+    a = predict._log_normmat(sh, 4, cpu)
+    assert predict._log_normmat(sh, 4, cpu) is a
+    sh.normmats[4] = sh.normmats[4] * 2.0
+    b = predict._log_normmat(sh, 4, cpu)
+    assert torch.allclose(b, a + np.log(2.0), atol=1e-6)
+    sh.normmats[4][10, 10] *= 3.0
+    c = predict._log_normmat(sh, 4, cpu)
+    assert c is not b and abs(float(c[0, 0, 10, 10] - b[0, 0, 10, 10]) - np.log(3.0)) < 1e-5
