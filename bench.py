@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--enc-fp16-stages", type=int, default=-1,
                     help="leading encoder stages in single-pass fp16 (0 = three-product bf16 everywhere; default: library default, 3)")
-    ap.add_argument("--cascade-mode", default=None, choices=["streams", "batch"])
+    ap.add_argument("--cascade-mode", default=None, choices=["serial", "batch"])
     ap.add_argument("--chunk-bp", type=int, default=0, help="encoder chunk length in bp (0 = library default)")
     ap.add_argument("--concurrent-strands", action="store_true", help="encode the two strands on two CUDA streams")
     args = ap.parse_args()
@@ -204,7 +204,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_impl(args.kernels)
-    enc16 = _lib.set_encoder_fp16_stages(args.enc_fp16_stages)  # returns the previous (= default) setting
+    enc16 = _lib.set_encoder_fp16_stages(args.enc_fp16_stages)  # returns the previous (= default) setting, 3
     if args.enc_fp16_stages >= 0:
         enc16 = min(args.enc_fp16_stages, 7)
     peaks = load_peaks()

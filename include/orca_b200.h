@@ -22,9 +22,12 @@
  * Conventions
  *   - plain C types only; every tensor is a raw DEVICE pointer to fp32 unless stated
  *     otherwise; shapes and strides (in ELEMENTS) are explicit.
- *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*);
- *     no hidden synchronisation, no global mutable state besides the last-error string
- *     (thread local).
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation.  Kernel selection and precision are properties of a module HANDLE
+ *     (orca_b200_module_set_option), never of the process: forwards on different handles are
+ *     independent and reentrant across host threads and streams.  The only process-wide state is
+ *     the launch counter (atomic), the thread-local last-error string and the opt-in, single-threaded
+ *     benchmarking recorder (orca_b200_profile_enable).
  *   - the caller owns inputs, outputs and workspace (allocated through its own
  *     allocator, e.g. PyTorch's); the library owns only the packed weights inside a
  *     module handle (released by orca_b200_module_destroy).
@@ -69,7 +72,7 @@ enum {
 #define ORCA_B200_UPSAMPLE_NEAREST 0u  /* Decoder(upsample_mode='nearest')  */
 #define ORCA_B200_UPSAMPLE_BILINEAR 1u /* Decoder(upsample_mode='bilinear'), align_corners=False */
 
-/* compute path selection (orca_b200_set_impl); both are CUDA, there is no CPU path */
+/* compute path selection (ORCA_B200_OPT_IMPL); both are CUDA, there is no CPU path */
 #define ORCA_B200_IMPL_AUTO 0  /* tcgen05 tensor-core kernels where available, else SIMT */
 #define ORCA_B200_IMPL_SIMT 1  /* fp32 CUDA-core implicit-GEMM everywhere */
 #define ORCA_B200_IMPL_TC 2    /* require the tcgen05 path (error if a layer lacks it) */
@@ -99,24 +102,26 @@ typedef struct orca_b200_module orca_b200_module;
 /* library / device */
 const char* orca_b200_version(void);
 const char* orca_b200_last_error(void);
-int orca_b200_set_impl(int impl);
-int orca_b200_get_impl(void);
 /*
- * Decoder scheduling.  1 (default): all 3x3 convs of a decoder call run as ONE persistent cooperative kernel
- * with grid barriers between layers (lowest latency for a single cascade).  0: one launch per conv, which lets
- * independent cascades on different CUDA streams interleave (cooperative kernels would serialise).
- * -1 restores the default.  Returns the previous setting.
+ * Per-handle options.
+ *   ORCA_B200_OPT_IMPL                 ORCA_B200_IMPL_* (default AUTO).
+ *   ORCA_B200_OPT_ENCODER_FP16_STAGES  Encoder / Net handles: the first n of the Encoder's 7 stages
+ *       (orca_modules.py:811-927) run their convolutions as ONE fp16 tensor-core product with fp16 activations; the
+ *       remaining stages -- and every other module -- keep fp32-grade arithmetic (operands split into two bf16, three
+ *       products).  Default 3: stages 1-3 hold 97 % of the encoder FLOP and their 2^-12 rounding noise is averaged out
+ *       by stages 4-7.  0 = three products everywhere; -1 restores the default.
+ * orca_b200_module_status reads (and optionally clears) the handle's device status word; it synchronises the device.
+ *   bit 0  ORCA_B200_STATUS_FP16_RANGE: a value written by a single-pass fp16 stage exceeded the fp16 range guard
+ *          (|x| > 60000) since the word was last cleared -- the output of that forward is not trustworthy; rerun it
+ *          with ORCA_B200_OPT_ENCODER_FP16_STAGES = 0 (orca_b200.modules does this automatically).
  */
-int orca_b200_set_decoder_program(int on);
-/*
- * Encoder precision.  The first `n` of the Encoder's 7 stages (orca_modules.py:811-927) run their convolutions as
- * ONE fp16 tensor-core product with fp16 activations; the remaining stages -- and every other module -- keep
- * fp32-grade arithmetic (operands split into two bf16, three products).  Default 3: stages 1-3 hold 97 % of the
- * encoder FLOP, and their 2^-12 rounding noise is averaged out by stages 4-7 (measured encoder-output error
- * unchanged at <= 1e-5 of the maximum).  n = 0 gives the three-product path everywhere,
- * n = 7 the fastest encoder (error ~3e-4).  -1 restores the default.  Returns the previous setting.
- */
-int orca_b200_set_encoder_fp16_stages(int n);
+#define ORCA_B200_OPT_IMPL 1
+#define ORCA_B200_OPT_ENCODER_FP16_STAGES 2
+#define ORCA_B200_STATUS_FP16_RANGE 1u
+int orca_b200_module_set_option(orca_b200_module* m, int option, int value);
+int orca_b200_module_get_option(const orca_b200_module* m, int option);
+int orca_b200_module_status(const orca_b200_module* m, uint32_t* status, int32_t clear);
+
 /* number of kernel launches issued by this library since load (all threads) */
 uint64_t orca_b200_launch_count(void);
 

@@ -13,6 +13,8 @@ OK = 0
 ENCODER, ENCODER2, ENCODER2B, ENCODER3, DECODER, DECODER_1M, NET = 1, 2, 3, 4, 5, 6, 7
 UPSAMPLE_NEAREST, UPSAMPLE_BILINEAR = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+OPT_IMPL, OPT_ENCODER_FP16_STAGES = 1, 2
+STATUS_FP16_RANGE = 1
 
 _fp = ctypes.POINTER(ctypes.c_float)
 _i64 = ctypes.c_int64
@@ -36,11 +38,10 @@ class ConvParams(ctypes.Structure):
 SIGNATURES = {
     "orca_b200_version": (ctypes.c_char_p, []),
     "orca_b200_last_error": (ctypes.c_char_p, []),
-    "orca_b200_set_impl": (ctypes.c_int, [ctypes.c_int]),
-    "orca_b200_get_impl": (ctypes.c_int, []),
     "orca_b200_launch_count": (ctypes.c_uint64, []),
-    "orca_b200_set_decoder_program": (ctypes.c_int, [ctypes.c_int]),
-    "orca_b200_set_encoder_fp16_stages": (ctypes.c_int, [ctypes.c_int]),
+    "orca_b200_module_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "orca_b200_module_get_option": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "orca_b200_module_status": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32]),
     "orca_b200_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "orca_b200_profile_summary": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_int64]),
     "orca_b200_module_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ConvParams), ctypes.c_int32,
@@ -96,13 +97,47 @@ def check(status):
         raise RuntimeError("orca_b200 error %d: %s" % (status, (msg or b"?").decode("utf-8", "replace")))
 
 
+# Python-side defaults applied to module handles (orca_b200.modules._NativeModule.native_handle): the C library itself
+# keeps kernel selection and precision per handle.  `options_epoch` changes whenever a default changes, so existing
+# modules re-apply the options before their next forward.
+_defaults = {"impl": IMPL_AUTO, "encoder_fp16_stages": -1}
+options_epoch = 0
+
+
 def set_impl(impl):
-    check(lib().orca_b200_set_impl({"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC}.get(impl, impl)))
+    """Default kernel family for every module: "auto" (tcgen05 where available), "simt" (fp32 CUDA cores), "tc"."""
+    global options_epoch
+    v = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC}.get(impl, impl)
+    if v not in (IMPL_AUTO, IMPL_SIMT, IMPL_TC):
+        raise ValueError("unknown impl %r" % (impl,))
+    _defaults["impl"] = v
+    options_epoch += 1
 
 
 def set_encoder_fp16_stages(n):
-    """Leading encoder stages in single-pass fp16 (0..7, -1 = default 3); returns the previous setting."""
-    return int(lib().orca_b200_set_encoder_fp16_stages(int(n)))
+    """Default number of leading encoder stages in single-pass fp16 (0..7, -1 = library default 3); returns the
+    previous effective setting."""
+    global options_epoch
+    prev = _defaults["encoder_fp16_stages"]
+    _defaults["encoder_fp16_stages"] = -1 if n < 0 else min(int(n), 7)
+    options_epoch += 1
+    return 3 if prev < 0 else prev
+
+
+def apply_options(handle, overrides=None):
+    """Push the defaults (plus a module's own overrides) into a native handle."""
+    opts = dict(_defaults)
+    if overrides:
+        opts.update(overrides)
+    check(lib().orca_b200_module_set_option(handle, OPT_IMPL, opts["impl"]))
+    check(lib().orca_b200_module_set_option(handle, OPT_ENCODER_FP16_STAGES, opts["encoder_fp16_stages"]))
+
+
+def module_status(handle, clear=True):
+    """Device status word of a handle (synchronises): bit 0 = the fp16 range guard fired."""
+    st = ctypes.c_uint32(0)
+    check(lib().orca_b200_module_status(handle, ctypes.byref(st), 1 if clear else 0))
+    return int(st.value)
 
 
 def launch_count():

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liborca_b200.so")
-SOURCES = ["modules.cu", "conv_simt.cu", "conv_tc.cu", "conv_first_tc.cu", "conv2d_tc.cu", "conv2d_prog.cu", "tc_glue.cu", "glue.cu"]
+SOURCES = ["modules.cu", "conv_simt.cu", "conv_tc.cu", "conv_first_tc.cu", "conv2d_stream.cu", "dec_glue.cu", "tc_glue.cu", "glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -41,7 +41,7 @@ using namespace tcdev;
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsS = 32 * (3 + kEpiWarps);
-constexpr int kMaxNA = 3;
+constexpr int kMaxNA = 4;
 constexpr int kAcc = 4;              // TMEM accumulator slots of 128 columns
 constexpr int kSmemCarve = 230400;   // 225 KB of operand / staging space (1024-aligned base; barriers + bias above it)
 constexpr int kSmemTotal = kSmemCarve + 1024 + 896;  // + 64 B of static shared memory (diagnostics) = 227 KB
@@ -55,7 +55,7 @@ struct SLayer {
   int c_in, c_out, d, relu;
   int in_c0, in_c1;           // inner (channel) coordinates of the hi and lo input boxes (c_in = 32: one box, in_c1 unused)
   int in_layer, res_layer, war_layer;
-  int NA, NS, drain_before;
+  int NA, NS, drain_before, rot;
   int offW, offA, offStg0, offStg1;
   int a_box_bytes, a_slot_bytes, w_bytes, R;
 };
@@ -156,15 +156,27 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t lo) { return ((uint64_t)
 // residue r = y mod d first, then k = y div d.  A segment = consecutive tiles of one chain, rows r + k*d, k0 <= k < k1.
 struct Seg { int b, tx, r, k0, k1, len; };
 struct Walk {
-  int S, d, q, rem, tpr, cur, end;
-  __device__ __forceinline__ void init(const SGeom& g, int d_) {
+  int S, d, q, rem, tpr, cur, end, n_tiles;
+  int cur2, end2;  // second piece of the rotated range
+  // The CTA's contiguous range [t0, t1) is walked from t0 + rot: [t0 + rot, t1) then [t0, t0 + rot).  Consecutive layers
+  // with the same dilation advance `rot` by 2, so the first tiles of a layer depend only on tiles the previous layer
+  // finished EARLY (its 2nd..4th), never on the ones it has just stored -- the store -> flag -> load latency of the
+  // dependent chain is then hidden behind the rest of the range instead of stalling every layer boundary.
+  __device__ __forceinline__ void init(const SGeom& g, int d_, int rot) {
     S = g.S; d = d_; tpr = g.tpr;
     q = S / d; rem = S - q * d;
-    cur = (int)(((long long)blockIdx.x * g.total_tiles) / gridDim.x);
-    end = (int)(((long long)(blockIdx.x + 1) * g.total_tiles) / gridDim.x);
+    const int t0 = (int)(((long long)blockIdx.x * g.total_tiles) / gridDim.x);
+    const int t1 = (int)(((long long)(blockIdx.x + 1) * g.total_tiles) / gridDim.x);
+    n_tiles = t1 - t0;
+    const int sft = n_tiles > 0 ? rot % n_tiles : 0;
+    cur = t0 + sft; end = t1;
+    cur2 = t0; end2 = t0 + sft;
   }
   __device__ __forceinline__ bool next(Seg& s) {
-    if (cur >= end) return false;
+    if (cur >= end) {
+      if (cur2 >= end2) return false;
+      cur = cur2; end = end2; cur2 = end2;
+    }
     const int img = cur / S, p = cur - img * S;
     s.b = img / tpr; s.tx = img - s.b * tpr;
     int k;
@@ -250,8 +262,8 @@ __device__ __forceinline__ void producer_layer(const SLayer& L, int l, const SGe
   const uint32_t slot_tx = (uint32_t)(L.c_in == 64 ? 2 : 1) * (uint32_t)L.R * 128u;
   const uint32_t stg_tx = (uint32_t)L.c_out * 4u * 128u;  // 128 pixels x (hi + lo) x c_out x 2 B
   Walk w;
-  w.init(g, L.d);
-  if (!L.tm_res) stg.skip(L.NS, (uint32_t)(w.end - w.cur));
+  w.init(g, L.d, L.rot);
+  if (!L.tm_res) stg.skip(L.NS, (uint32_t)w.n_tiles);
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
@@ -330,7 +342,7 @@ __device__ __forceinline__ void mma_layer(const SLayer& L, int l, const SGeom& g
   const uint32_t bBase = umma_desc_lo(smem0 + L.offW, 2 * C_OUT * 16);
   const uint32_t dshift = ((uint32_t)L.d * 128u) >> 4;
   Walk w;
-  w.init(g, L.d);
+  w.init(g, L.d, L.rot);
   Seg s;
   while (w.next(s)) {
     const int k_first = run_first(s), k_last = run_last(s);
@@ -388,7 +400,7 @@ __device__ __forceinline__ void epilogue_layer(const SLayer& L, const SGeom& g, 
   const int row = q * 32 + lane;           // pixel within the tile = TMEM lane
   const uint32_t sw = (uint32_t)(row & 7);
   Walk w;
-  w.init(g, L.d);
+  w.init(g, L.d, L.rot);
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
@@ -457,7 +469,7 @@ __device__ __forceinline__ void store_layer(const SLayer& L, int l, const SGeom&
   __syncwarp();
   unsigned int* flags = g.flags + (size_t)l * g.nb * g.S;
   Walk w;
-  w.init(g, L.d);
+  w.init(g, L.d, L.rot);
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
@@ -751,6 +763,8 @@ int DecStream::add(const ConvLayer& L, int k_half, int use_bias, const DMap& in,
     t.drain_before = hit ? 1 : 0;
   }
   impl->stg0_prev = t.offStg0; impl->stg1_prev = t.offStg1; impl->stg_size_prev = stg_size; impl->ns_prev = t.NS;
+  // rotation of the tile walk: +2 per consecutive layer with the same dilation (see Walk)
+  t.rot = (l > 0 && impl->layers[l - 1].d == t.d) ? impl->layers[l - 1].rot + 2 : 0;
   // ---- dependencies ----
   auto find = [](const std::map<const void*, int>& m, const void* p) { auto it = m.find(p); return it == m.end() ? -1 : it->second; };
   t.in_layer = find(impl->last_writer, in.p);

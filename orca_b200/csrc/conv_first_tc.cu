@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
                                                         int npad, const uint8_t* __restrict__ wimg /*[10][128 | 64][16 B]*/,
                                                         const float* __restrict__ bias,
                                                         __nv_bfloat16* __restrict__ out_hi,
-                                                        __nv_bfloat16* __restrict__ out_lo) {
+                                                        __nv_bfloat16* __restrict__ out_lo, unsigned int* sat) {
   extern __shared__ __align__(128) uint8_t dsm[];  // operand images (dynamic: above the 48 KB static limit)
   constexpr int kBRows = F16 ? 64 : 128;          // weight rows per K chunk: [B] or [Bh | Bl]
   constexpr uint32_t kTmemCols = F16 ? 64 : 128;
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(128) lconv1_tc_kernel(const SeqIn in, long lon
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + (F16 ? 0.f : __uint_as_float(r1[j])) + sBias[c0 + j];
+      if (!out_lo) guard_h<32>(v, sat);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const size_t off = (((size_t)b * 8 + (c0 >> 3) + ch) * npad + row + 4) * 8;
@@ -287,11 +288,11 @@ int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb,
   }
   if (f16)
     lconv1_tc_kernel<true><<<grid, 128, kSmem16, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w16),
-                                                    L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), nullptr);
+                                                    L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi), nullptr, out->sat);
   else
     lconv1_tc_kernel<false><<<grid, 128, kSmem, s>>>(in, Ltot, l_begin, n, (int)out->npad, static_cast<const uint8_t*>(L0.tc_w),
                                                      L0.tc_bias, static_cast<__nv_bfloat16*>(out->hi),
-                                                     out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo));
+                                                     out->fmt ? nullptr : static_cast<__nv_bfloat16*>(out->lo), nullptr);
   ORCA_LAUNCH_OK();
   if (l_begin == 0 || l_begin + n == Ltot) {
     lconv1_edge_kernel<<<dim3(2, (unsigned)nb), 64, 0, s>>>(in, Ltot, l_begin, n, (int)out->npad, L0.w, L0.b, L1.w, L1.b,

@@ -51,6 +51,7 @@ struct TcKArgs {
   const __nv_bfloat16* res2_hi; const __nv_bfloat16* res2_lo;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   float* out_f32;
+  unsigned int* sat;  // fp16 range guard word (FMT 1 outputs), or nullptr
   int nb, n, npad_in, n_out, npad_out, pool, relu;
   int tiles_per_sample, total_tiles;
 };
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
 #pragma unroll
           for (int j = 0; j < 32; ++j) rcur[j] = rnext[j];
         }
+        if (FMT && a.out_hi && !a.out_lo) guard_h<32>(v, a.sat);
         if (FMT && a.pool > 1 && a.out_hi && !a.out_lo) {
           // Fused max-pool of the single-pass format through shared memory.  TMEM lane = position, so pooling over
           // 2 / 4 neighbouring positions with warp shuffles costs ~4 instructions per value and made the residual+pool
@@ -616,6 +618,7 @@ int tc_conv1d(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_
   a.out_hi = out_planes ? static_cast<__nv_bfloat16*>(out_planes->hi) : nullptr;
   a.out_lo = (out_planes && out_planes->fmt == 0) ? static_cast<__nv_bfloat16*>(out_planes->lo) : nullptr;  // NULL: one fp16 plane
   a.out_f32 = out_f32;
+  a.sat = (out_planes && out_planes->fmt == 1) ? out_planes->sat : nullptr;
   a.nb = in.nb; a.n = (int)in.n; a.npad_in = (int)in.npad; a.n_out = (int)(in.n / pool);
   a.npad_out = out_planes ? (int)out_planes->npad : 0;
   a.pool = pool; a.relu = relu;

@@ -12,13 +12,21 @@
 
 #include "common.h"
 #include "tc.h"
+#include "dec_stream.h"
 #include "seq_in.cuh"
 
 namespace orca {
 
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_impl{ORCA_B200_IMPL_AUTO};
+// Options of the module handle a forward call was made on (orca_b200_module_set_option), copied into thread-local
+// storage for the duration of the call: kernel selection and precision are per handle, never process-global.
+struct CallOpts {
+  int impl = ORCA_B200_IMPL_AUTO;
+  int enc_fp16_stages = -1;        // -1 = default (3)
+  unsigned int* status = nullptr;  // device status word of the handle (bit 0: fp16 range guard fired)
+};
+static thread_local CallOpts t_opts;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -95,9 +103,22 @@ struct orca_b200_module {
   int num_1d = 0;
   int num_2d = 1;  // output maps of Decoder / Decoder_1m / Net
   int device = 0;
+  int impl = ORCA_B200_IMPL_AUTO;   // ORCA_B200_OPT_IMPL
+  int enc_fp16_stages = -1;         // ORCA_B200_OPT_ENCODER_FP16_STAGES (-1 = default)
+  unsigned int* d_status = nullptr; // device word, see orca_b200_module_status
   std::vector<ConvLayer> L;
   std::vector<void*> allocs;
 };
+
+namespace orca {
+struct CallScope {  // RAII: the handle's options are the calling thread's options while one of its forwards runs
+  CallOpts saved;
+  explicit CallScope(const orca_b200_module* m) : saved(t_opts) {
+    if (m) { t_opts.impl = m->impl; t_opts.enc_fp16_stages = m->enc_fp16_stages; t_opts.status = m->d_status; }
+  }
+  ~CallScope() { t_opts = saved; }
+};
+}  // namespace orca
 
 namespace orca {
 
@@ -129,7 +150,7 @@ static int conv(const ConvLayer& L, const ConvCall& c, cudaStream_t s) {
 }
 
 static int conv_dispatch(const ConvLayer& L, const ConvCall& c, cudaStream_t s, bool* used_tc) {
-  const int impl = g_impl.load(std::memory_order_relaxed);
+  const int impl = t_opts.impl;
   *used_tc = false;
   if (impl != ORCA_B200_IMPL_SIMT && tc_supported(L, c)) { *used_tc = true; return conv_tc(L, c, s); }
   if (impl == ORCA_B200_IMPL_TC) {
@@ -223,20 +244,17 @@ static TcAct tc_make(void* base, int nb, int C, int64_t n, int fmt = 0) {
   t.nb = nb; t.C = C; t.n = n; t.npad = tc_npad(n); t.fmt = fmt;
   t.hi = base;
   t.lo = (base && !fmt) ? static_cast<char*>(base) + tc_plane_bytes(nb, C, n) : nullptr;
+  t.sat = fmt ? t_opts.status : nullptr;
   return t;
 }
 
 // Number of leading encoder stages that run in the single-pass fp16 format (conv_tc.cu, FMT = 1); the rest, the
 // U-nets and the decoders keep the three-product bf16 hi/lo format.  -1 = default (env ORCA_B200_ENC_FP16_STAGES,
 // else 3: stages 1-3 are 97 % of the encoder FLOP and their rounding noise does not survive stages 4-7).
-static std::atomic<int> g_enc_fp16_stages{-1};
 static int encoder_fp16_stages() {
-  int v = g_enc_fp16_stages.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = getenv("ORCA_B200_ENC_FP16_STAGES");
-    v = e ? atoi(e) : 3;
-  }
-  return v < 0 ? 0 : (v > 7 ? 7 : v);
+  int v = t_opts.enc_fp16_stages;
+  if (v < 0) v = 3;
+  return v > 7 ? 7 : v;
 }
 
 static int tc_conv1d_prof(const ConvLayer& L, const TcAct& in, const TcAct* res, TcAct* out_planes, float* out_f32,
@@ -307,7 +325,7 @@ static int encoder_window_tc(const ConvLayer* L, const SeqIn& x, int nb, int64_t
 }
 
 static bool use_tc_encoder(const ConvLayer* L) {
-  if (g_impl.load(std::memory_order_relaxed) == ORCA_B200_IMPL_SIMT) return false;
+  if (t_opts.impl == ORCA_B200_IMPL_SIMT) return false;
   for (int i = 1; i < 28; ++i)
     if (!L[i].tc_w) return false;
   return true;
@@ -493,7 +511,7 @@ static int unet_run_tc(const orca_b200_module* m, const float* x, int64_t B, int
 
 static int unet_run_any(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
                         int64_t sL, float* const* outs, int n_out, int coarsest_only, Arena& ar, cudaStream_t s) {
-  bool tc = g_impl.load(std::memory_order_relaxed) != ORCA_B200_IMPL_SIMT;
+  bool tc = t_opts.impl != ORCA_B200_IMPL_SIMT;
   for (const ConvLayer& l : m->L) tc = tc && l.tc_w;
   if (tc) return unet_run_tc(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, s);
   return unet_run(m, x, B, P, sB, sC, sL, outs, n_out, coarsest_only, ar, s);
@@ -606,151 +624,142 @@ static int decoder_body(const orca_b200_module* m, const ConvLayer* L, bool is_1
   return ORCA_B200_OK;
 }
 
-// ---- the same decoder programs on the tcgen05 path (activations as bf16 hi/lo map planes, tc.h) ----
-// When a decoder program is being recorded (conv2d_prog.cu) the conv is appended to it instead of launched.
-static thread_local Tc2dProgram* t_prog = nullptr;
-
-// -1 = take the default (env ORCA_B200_DEC_PROGRAM, else on); set by orca_b200_set_decoder_program
-static std::atomic<int> g_dec_program{-1};
-
-static bool use_decoder_program() {
-  int v = g_dec_program.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = getenv("ORCA_B200_DEC_PROGRAM");
-    v = e ? atoi(e) : 1;
+// ---- the same decoder programs on the tcgen05 path: ONE persistent stream kernel per call (dec_stream.h) ----
+// Buffer plan.  Every conv output goes to a pool buffer that no layer of the last two reads (the kernel recycles a
+// buffer only when every CTA has finished its last reader, conv2d_stream.cu); among those the most recently used one
+// is taken, so the main loop cycles through 2 x 64-channel + 2 x 32-channel maps (96 MB at batch 2: L2 resident).
+struct MapPool {
+  std::vector<DMap> bufs;
+  std::vector<int> last_use;  // layer index of the last read or write
+  int pick(int layer, const void* k0, const void* k1, const void* k2) {
+    int best = -1;
+    for (int pass = 0; pass < 2 && best < 0; ++pass)
+      for (size_t i = 0; i < bufs.size(); ++i) {
+        const void* p = bufs[i].p;
+        if (p == k0 || p == k1 || p == k2) continue;
+        if (pass == 0 && last_use[i] > layer - 2) continue;  // still being read by the previous layer
+        if (best < 0 || (pass == 0 ? last_use[i] > last_use[best] : last_use[i] < last_use[best])) best = (int)i;
+      }
+    return best;
   }
-  return v != 0;
-}
-
-static int tc_conv2d_prof(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s) {
-  if (t_prog) return t_prog->add(L, in, res, out, relu);
-  if (!g_profile.load(std::memory_order_relaxed)) return tc_conv2d(L, in, res, out, relu, s);
-  ProfRec r;
-  ORCA_CUDA_OK(cudaEventCreate(&r.e0));
-  ORCA_CUDA_OK(cudaEventCreate(&r.e1));
-  ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
-  const int st = tc_conv2d(L, in, res, out, relu, s);
-  ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
-  r.c_in = L.c_in; r.c_out = L.c_out; r.taps = 9; r.dil = L.dil; r.tc = 1;
-  r.flop = 2.0 * (double)in.nb * in.S * in.S * L.c_in * L.c_out * 9;
-  g_prof.push_back(r);
-  return st;
-}
-
-static TcMap map_make(void* base, int nb, int C, int S) {
-  TcMap t;
-  t.nb = nb; t.C = C; t.S = S; t.Wp = S + 128; t.plane_rows = tc2d_plane_rows(S);
-  t.hi = base;
-  t.lo = base ? static_cast<char*>(base) + tc2d_plane_bytes(nb, C, S) : nullptr;
-  return t;
-}
-
-struct MapRot {
-  void* buf[3];
-  int cur = 0, nb = 0, S = 0;
-  TcMap next(int C = 64) { cur = (cur + 1) % 3; return map_make(buf[cur], nb, C, S); }
+  void touch(const void* p, int layer) {
+    for (size_t i = 0; i < bufs.size(); ++i)
+      if (bufs[i].p == p) last_use[i] = layer;
+  }
 };
 
-// cur = lm(cur) [+ cur] ; cur = m(cur) + cur   (one residual bottleneck unit)
-static int bottleneck_tc(const ConvLayer* lm, const ConvLayer* mm, TcMap& cur, bool l_residual, MapRot& rot, void* hbuf,
-                         cudaStream_t s) {
-  TcMap h = map_make(hbuf, cur.nb, lm[0].c_out, cur.S);
-  ORCA_TRY(tc_conv2d_prof(lm[0], cur, nullptr, &h, 0, s));
-  TcMap t1 = rot.next();
-  ORCA_TRY(tc_conv2d_prof(lm[1], h, l_residual ? &cur : nullptr, &t1, 0, s));
-  TcMap h2 = map_make(hbuf, cur.nb, mm[0].c_out, cur.S);
-  ORCA_TRY(tc_conv2d_prof(mm[0], t1, nullptr, &h2, 1, s));
-  TcMap t2 = rot.next();
-  ORCA_TRY(tc_conv2d_prof(mm[1], h2, &t1, &t2, 1, s));
-  cur = t2;
-  return ORCA_B200_OK;
-}
+struct StreamBuilder {
+  DecStream prog;
+  MapPool x64, t32;
+  // out = act(conv(in) + b) [+ res]; `keep` = a map that must survive this layer (a later residual)
+  int conv(const ConvLayer& L, const DMap& in, const DMap* res, const DMap* keep, int relu, DMap* out) {
+    const int l = prog.size();
+    MapPool& pool = L.c_out == 32 ? t32 : x64;
+    if (L.c_in == 128) {  // two 64-channel K halves chained through the residual; bias with the second
+      const int i0 = pool.pick(l, in.p, res ? res->p : nullptr, keep ? keep->p : nullptr);
+      if (i0 < 0) { set_error("decoder: map pool exhausted"); return ORCA_B200_EWORKSPACE; }
+      DMap mid = pool.bufs[i0];
+      ORCA_TRY(prog.add(L, 0, 0, in, res, &mid, 0));
+      pool.touch(mid.p, l);
+      if (res) x64.touch(res->p, l), t32.touch(res->p, l);
+      const int i1 = pool.pick(l + 1, in.p, mid.p, keep ? keep->p : nullptr);
+      if (i1 < 0) { set_error("decoder: map pool exhausted"); return ORCA_B200_EWORKSPACE; }
+      *out = pool.bufs[i1];
+      ORCA_TRY(prog.add(L, 1, 1, in, &mid, out, relu));
+      pool.touch(mid.p, l + 1);
+      pool.touch(out->p, l + 1);
+      return ORCA_B200_OK;
+    }
+    const int i = pool.pick(l, in.p, res ? res->p : nullptr, keep ? keep->p : nullptr);
+    if (i < 0) { set_error("decoder: map pool exhausted"); return ORCA_B200_EWORKSPACE; }
+    *out = pool.bufs[i];
+    ORCA_TRY(prog.add(L, -1, 1, in, res, out, relu));
+    x64.touch(in.p, l); t32.touch(in.p, l);
+    if (res) x64.touch(res->p, l), t32.touch(res->p, l);
+    pool.touch(out->p, l);
+    return ORCA_B200_OK;
+  }
+  // cur = lm(cur) [+ cur] ; cur = m(cur) + cur   (one residual bottleneck unit)
+  int bottleneck(const ConvLayer* lm, const ConvLayer* mm, DMap& cur, bool l_residual) {
+    DMap h, t1, h2, t2;
+    ORCA_TRY(conv(lm[0], cur, nullptr, &cur, 0, &h));
+    ORCA_TRY(conv(lm[1], h, l_residual ? &cur : nullptr, nullptr, 0, &t1));
+    ORCA_TRY(conv(mm[0], t1, nullptr, &t1, 1, &h2));
+    ORCA_TRY(conv(mm[1], h2, &t1, nullptr, 1, &t2));
+    cur = t2;
+    return ORCA_B200_OK;
+  }
+};
 
 static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool is_1m, const float* xcl, int B, int S,
                            const Plane4& de, const Plane4& yc, float* out, Arena& ar, cudaStream_t s) {
   const float* distenc = de.p;
   const float* y = yc.p;
   const size_t mk = ar.mark();
-  const size_t b64 = 2 * tc2d_plane_bytes(B, 64, S);
+  const size_t b64 = dmap_bytes(B, 64, S);
   void* matb = ar.raw(2 * b64);  // 128 channels
-  MapRot rot;
-  rot.nb = B; rot.S = S;
-  rot.buf[0] = ar.raw(b64); rot.buf[1] = ar.raw(b64); rot.buf[2] = ar.raw(b64);
-  void* hbuf = ar.raw(b64);
-  void* ebuf = is_1m ? nullptr : ar.raw(b64);
-  void* ebuf2 = is_1m ? nullptr : ar.raw(b64);  // coarse-map term (kept apart from the distance term: both are
-                                                // computed before the conv program runs)
+  void* xb[3] = {ar.raw(b64), ar.raw(b64), ar.raw(b64)};
+  void* tb[2] = {ar.raw(b64 / 2), ar.raw(b64 / 2)};
+  void* ebuf = is_1m ? nullptr : ar.raw(b64);   // distance-encoding term of lcombinerD (extra input channels)
+  void* ebuf2 = is_1m ? nullptr : ar.raw(b64);  // coarse-map term of lcombiner
   float* tmp = ar.f32((size_t)B * S * S * m->num_2d);
-  const size_t prog_bytes = Tc2dProgram::scratch_bytes(128);
+  const size_t prog_bytes = DecStream::scratch_bytes(128, B, S);
   void* prog_scratch = ar.raw(prog_bytes);
   ARENA_OK(ar);
   if (!ar.dry) {
-    Tc2dProgram prog;
-    struct ProgGuard { ~ProgGuard() { t_prog = nullptr; } } guard;  // never leave a dangling recorder on error paths
-    t_prog = use_decoder_program() ? &prog : nullptr;
-    auto flush = [&]() -> int {  // run the recorded convs (program mode) before anything reads their output
-      if (!t_prog) return ORCA_B200_OK;
-      t_prog = nullptr;
-      if (!g_profile.load(std::memory_order_relaxed)) return prog.run(prog_scratch, prog_bytes, s);
-      ProfRec r;
-      ORCA_CUDA_OK(cudaEventCreate(&r.e0));
-      ORCA_CUDA_OK(cudaEventCreate(&r.e1));
-      ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
-      const int st = prog.run(prog_scratch, prog_bytes, s);
-      ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
-      r.c_in = -1; r.c_out = prog.size(); r.taps = 9; r.dil = 1; r.tc = 1; r.flop = prog.flop();
-      g_prof.push_back(r);
-      return st;
-    };
-    // pad pixels of every map must be zero; the layers only ever write valid pixels
-    ORCA_CUDA_OK(cudaMemsetAsync(matb, 0, 2 * b64, s));
-    for (int i = 0; i < 3; ++i) ORCA_CUDA_OK(cudaMemsetAsync(rot.buf[i], 0, b64, s));
-    ORCA_CUDA_OK(cudaMemsetAsync(hbuf, 0, b64, s));
-    if (ebuf) ORCA_CUDA_OK(cudaMemsetAsync(ebuf, 0, b64, s));
-    if (ebuf2) ORCA_CUDA_OK(cudaMemsetAsync(ebuf2, 0, b64, s));
-    TcMap mat = map_make(matb, B, 128, S);
-    ORCA_TRY(tc_outer_sum(xcl, &mat, s));
-    TcMap cur;
+    StreamBuilder sb;
+    for (int i = 0; i < 3; ++i) { sb.x64.bufs.push_back(dmap_make(xb[i], B, 64, S)); sb.x64.last_use.push_back(-100 + i); }
+    for (int i = 0; i < 2; ++i) { sb.t32.bufs.push_back(dmap_make(tb[i], B, 32, S)); sb.t32.last_use.push_back(-100 + i); }
+    DMap mat = dmap_make(matb, B, 128, S);
+    ORCA_TRY(ds_outer_sum(xcl, &mat, s));
+    DMap cur;
     if (is_1m) {
-      cur = mat;
-      ORCA_TRY(bottleneck_tc(L + D1M_LCONV, L + D1M_CONV, cur, false, rot, hbuf, s));
-      for (int i = 1; i < 19; ++i)
-        ORCA_TRY(bottleneck_tc(L + D1M_LCONV + 2 * i, L + D1M_CONV + 2 * i, cur, true, rot, hbuf, s));
-      ORCA_TRY(flush());
-      ORCA_TRY(tc_final_head_tmp(cur, L[D1M_FINAL], L[D1M_FINAL + 1], tmp, s));
+      cur = mat;  // first unit: 128 -> 32 -> 64, no residual on lm (orca_modules.py:789-792)
+      ORCA_TRY(sb.bottleneck(L + D1M_LCONV, L + D1M_CONV, cur, false));
+      for (int i = 1; i < 19; ++i) ORCA_TRY(sb.bottleneck(L + D1M_LCONV + 2 * i, L + D1M_CONV + 2 * i, cur, true));
     } else {
-      TcMap E = map_make(ebuf, B, 64, S);
-      ORCA_TRY(tc_extra_conv(distenc, de.sB, de.sC, de.sH, de.sW, L[DEC_LCOMBD].n_extra, L[DEC_LCOMBD].w_extra, &E, 0, s));
-      TcMap a0 = rot.next();
-      ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMBD], mat, &E, &a0, 0, s));
-      TcMap a1 = rot.next();
-      ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMBD + 1], a0, nullptr, &a1, 0, s));
-      TcMap a2 = rot.next();
-      ORCA_TRY(tc_conv2d_prof(L[DEC_COMBD], a1, nullptr, &a2, 1, s));
-      TcMap a3 = rot.next();
-      ORCA_TRY(tc_conv2d_prof(L[DEC_COMBD + 1], a2, &a1, &a3, 1, s));
+      // mat = lcombinerD(cat(mat, distenc)) ; mat = combinerD(mat) + mat      (orca_modules.py:463-465)
+      DMap E = dmap_make(ebuf, B, 64, S);
+      ORCA_TRY(ds_extra_conv(distenc, de.sB, de.sC, de.sH, de.sW, L[DEC_LCOMBD].n_extra, L[DEC_LCOMBD].w_extra, &E, 0, s));
+      DMap a0, a1, a2, a3;
+      ORCA_TRY(sb.conv(L[DEC_LCOMBD], mat, &E, nullptr, 0, &a0));
+      ORCA_TRY(sb.conv(L[DEC_LCOMBD + 1], a0, nullptr, nullptr, 0, &a1));
+      ORCA_TRY(sb.conv(L[DEC_COMBD], a1, nullptr, &a1, 1, &a2));
+      ORCA_TRY(sb.conv(L[DEC_COMBD + 1], a2, &a1, nullptr, 1, &a3));
       cur = a3;
       if (y) {
+        // cur = lcombiner(cat(mat, upsample(y))) ; cur = combiner(cur) + cur   (:467-474)
         const int mode = (m->flags & ORCA_B200_UPSAMPLE_BILINEAR) ? 2 : 1;
-        TcMap E2 = map_make(ebuf2, B, 64, S);
-        ORCA_TRY(tc_extra_conv(y, yc.sB, yc.sC, yc.sH, yc.sW, L[DEC_LCOMB].n_extra, L[DEC_LCOMB].w_extra, &E2, mode, s));
-        TcMap b0 = rot.next();
-        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB], cur, &E2, &b0, 0, s));
-        TcMap b1 = rot.next();
-        ORCA_TRY(tc_conv2d_prof(L[DEC_LCOMB + 1], b0, nullptr, &b1, 0, s));
-        TcMap b2 = rot.next();
-        ORCA_TRY(tc_conv2d_prof(L[DEC_COMB], b1, nullptr, &b2, 1, s));
-        TcMap b3 = rot.next();
-        ORCA_TRY(tc_conv2d_prof(L[DEC_COMB + 1], b2, &b1, &b3, 1, s));
+        DMap E2 = dmap_make(ebuf2, B, 64, S);
+        ORCA_TRY(ds_extra_conv(y, yc.sB, yc.sC, yc.sH, yc.sW, L[DEC_LCOMB].n_extra, L[DEC_LCOMB].w_extra, &E2, mode, s));
+        DMap b0, b1, b2, b3;
+        ORCA_TRY(sb.conv(L[DEC_LCOMB], cur, &E2, nullptr, 0, &b0));
+        ORCA_TRY(sb.conv(L[DEC_LCOMB + 1], b0, nullptr, nullptr, 0, &b1));
+        ORCA_TRY(sb.conv(L[DEC_COMB], b1, nullptr, &b1, 1, &b2));
+        ORCA_TRY(sb.conv(L[DEC_COMB + 1], b2, &b1, nullptr, 1, &b3));
         cur = b3;
       } else {
-        ORCA_TRY(bottleneck_tc(L + DEC_LCONV, L + DEC_CONV, cur, false, rot, hbuf, s));
+        // cur = lconvtwos[0](cur) ; cur = convtwos[0](cur) + cur               (:475-477)
+        ORCA_TRY(sb.bottleneck(L + DEC_LCONV, L + DEC_CONV, cur, false));
       }
-      for (int i = 1; i < 28; ++i)
-        ORCA_TRY(bottleneck_tc(L + DEC_LCONV + 2 * i, L + DEC_CONV + 2 * i, cur, true, rot, hbuf, s));
-      ORCA_TRY(flush());
-      ORCA_TRY(tc_final_head_tmp(cur, L[DEC_FINAL], L[DEC_FINAL + 1], tmp, s));
+      for (int i = 1; i < 28; ++i) ORCA_TRY(sb.bottleneck(L + DEC_LCONV + 2 * i, L + DEC_CONV + 2 * i, cur, true));  // (:479-485)
     }
+    {
+      ProfRec r{};
+      const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+      if (prof) {
+        ORCA_CUDA_OK(cudaEventCreate(&r.e0));
+        ORCA_CUDA_OK(cudaEventCreate(&r.e1));
+        ORCA_CUDA_OK(cudaEventRecord(r.e0, s));
+      }
+      ORCA_TRY(sb.prog.run(prog_scratch, prog_bytes, s));
+      if (prof) {
+        ORCA_CUDA_OK(cudaEventRecord(r.e1, s));
+        r.c_in = -1; r.c_out = sb.prog.size(); r.taps = 9; r.dil = 1; r.tc = 1; r.flop = sb.prog.flop();
+        g_prof.push_back(r);
+      }
+    }
+    ORCA_TRY(ds_final_head_tmp(cur, L[is_1m ? D1M_FINAL : DEC_FINAL], L[(is_1m ? D1M_FINAL : DEC_FINAL) + 1], tmp, s));
     ORCA_TRY(symmetrise(tmp, out, B * m->num_2d, S, s));
   }
   ar.release(mk);
@@ -758,7 +767,7 @@ static int decoder_body_tc(const orca_b200_module* m, const ConvLayer* L, bool i
 }
 
 static bool use_tc_decoder(const ConvLayer* L, bool is_1m) {
-  if (g_impl.load(std::memory_order_relaxed) == ORCA_B200_IMPL_SIMT) return false;
+  if (t_opts.impl == ORCA_B200_IMPL_SIMT) return false;
   const int n = is_1m ? D1M_N : DEC_N;
   for (int i = 0; i < n; ++i)
     if (L[i].kh == 3 && !L[i].tc_w) return false;
@@ -852,7 +861,7 @@ static int pack_layer(const orca_b200_conv_params& p, int n_extra, ConvLayer& L,
   ORCA_TRY(upload(bias, &L.b, allocs));
   if (odd) ORCA_TRY(upload(wx, &L.w_extra, allocs));
   ORCA_TRY(tc_pack_layer(L, w.data(), allocs));
-  ORCA_TRY(tc_pack_layer2d(L, w.data(), allocs));
+  ORCA_TRY(ds_pack_layer(L, w.data(), allocs));
   if (keep_w) *keep_w = w;
   if (keep_b) *keep_b = bias;
   return ORCA_B200_OK;
@@ -880,20 +889,33 @@ extern "C" {
 const char* orca_b200_version(void) { return "orca_b200 0.1 (sm_100a)"; }
 const char* orca_b200_last_error(void) { return t_error.c_str(); }
 uint64_t orca_b200_launch_count(void) { return g_launches.load(); }
-int orca_b200_get_impl(void) { return g_impl.load(); }
-int orca_b200_set_decoder_program(int on) {
-  const int prev = g_dec_program.load();
-  g_dec_program.store(on < 0 ? -1 : (on ? 1 : 0));
-  return prev;
+int orca_b200_module_set_option(orca_b200_module* m, int option, int value) {
+  if (!m) { set_error("module_set_option: NULL module"); return ORCA_B200_EINVAL; }
+  switch (option) {
+    case ORCA_B200_OPT_IMPL:
+      if (value < ORCA_B200_IMPL_AUTO || value > ORCA_B200_IMPL_TC) { set_error("module_set_option: unknown impl %d", value); return ORCA_B200_EINVAL; }
+      m->impl = value;
+      return ORCA_B200_OK;
+    case ORCA_B200_OPT_ENCODER_FP16_STAGES:
+      m->enc_fp16_stages = value < 0 ? -1 : (value > 7 ? 7 : value);
+      return ORCA_B200_OK;
+    default:
+      set_error("module_set_option: unknown option %d", option);
+      return ORCA_B200_EINVAL;
+  }
 }
-int orca_b200_set_encoder_fp16_stages(int n) {
-  const int prev = encoder_fp16_stages();
-  g_enc_fp16_stages.store(n < 0 ? -1 : (n > 7 ? 7 : n));
-  return prev;
+int orca_b200_module_get_option(const orca_b200_module* m, int option) {
+  if (!m) return ORCA_B200_EINVAL;
+  if (option == ORCA_B200_OPT_IMPL) return m->impl;
+  if (option == ORCA_B200_OPT_ENCODER_FP16_STAGES) return m->enc_fp16_stages < 0 ? 3 : m->enc_fp16_stages;
+  return ORCA_B200_EINVAL;
 }
-int orca_b200_set_impl(int impl) {
-  if (impl < ORCA_B200_IMPL_AUTO || impl > ORCA_B200_IMPL_TC) { set_error("set_impl: unknown impl %d", impl); return ORCA_B200_EINVAL; }
-  g_impl.store(impl);
+int orca_b200_module_status(const orca_b200_module* m, uint32_t* status, int32_t clear) {
+  if (!m || !status) { set_error("module_status: NULL argument"); return ORCA_B200_EINVAL; }
+  *status = 0;
+  if (!m->d_status) return ORCA_B200_OK;
+  ORCA_CUDA_OK(cudaMemcpy(status, m->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost));  // synchronises
+  if (clear && *status) ORCA_CUDA_OK(cudaMemset(m->d_status, 0, sizeof(uint32_t)));
   return ORCA_B200_OK;
 }
 
@@ -945,6 +967,12 @@ int orca_b200_module_create(int kind, const orca_b200_conv_params* convs, int32_
   if (!m) { set_error("module_create: out of host memory"); return ORCA_B200_EINVAL; }
   m->kind = kind; m->flags = flags; m->num_1d = num_1d; m->num_2d = num_2d;
   if (cudaGetDevice(&m->device) != cudaSuccess) { cudaGetLastError(); delete m; set_error("module_create: no CUDA device"); return ORCA_B200_ECUDA; }
+  {
+    void* st = nullptr;
+    if (cudaMalloc(&st, 256) != cudaSuccess || cudaMemset(st, 0, 256) != cudaSuccess) { cudaGetLastError(); delete m; set_error("module_create: cudaMalloc failed"); return ORCA_B200_ECUDA; }
+    m->allocs.push_back(st);
+    m->d_status = static_cast<unsigned int*>(st);
+  }
   m->L.resize(n_convs);
   std::vector<float> head_w[2], head_b[2];
   for (int i = 0; i < n_convs; ++i) {
@@ -977,6 +1005,7 @@ static int encoder_args_ok(const orca_b200_module* m, int64_t B, int64_t L, int6
 }
 
 size_t orca_b200_encoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L, int64_t chunk_bp) {
+  CallScope scope(m);
   if (encoder_args_ok(m, B, L, 0, L / kBin) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
   encoder_run(m, SeqIn(), B, L, nullptr, 0, L / kBin, chunk_bp, ar, nullptr);
@@ -986,6 +1015,7 @@ size_t orca_b200_encoder_workspace_bytes(const orca_b200_module* m, int64_t B, i
 static int encoder_forward_common(const orca_b200_module* m, SeqIn in, int64_t B, int64_t L, int64_t x_pos0, int64_t x_len,
                                   float* out, int64_t bin_begin, int64_t bin_end, int64_t chunk_bp, void* workspace,
                                   size_t workspace_bytes, void* stream) {
+  CallScope scope(m);
   ORCA_TRY(encoder_args_ok(m, B, L, bin_begin, bin_end));
   ORCA_TRY(check_ptr_device(in.bases ? static_cast<const void*>(in.bases) : static_cast<const void*>(in.x), "encoder: x"));
   ORCA_TRY(check_ptr_device(out, "encoder: out"));
@@ -1041,6 +1071,7 @@ static int unet_args_ok(const orca_b200_module* m, int64_t B, int64_t P, int n_o
 }
 
 size_t orca_b200_encoder2_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t P) {
+  CallScope scope(m);
   if (!m) return 0;
   const int n_out = m->kind == ORCA_B200_ENCODER3 ? 4 : 6;
   if (unet_args_ok(m, B, P, n_out) != ORCA_B200_OK) return 0;
@@ -1056,6 +1087,7 @@ size_t orca_b200_encoder2_workspace_bytes(const orca_b200_module* m, int64_t B, 
 int orca_b200_encoder2_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t P, int64_t sB, int64_t sC,
                                int64_t sL, float* const* outs, int32_t n_out, int32_t coarsest_only, void* workspace,
                                size_t workspace_bytes, void* stream) {
+  CallScope scope(m);
   ORCA_TRY(unet_args_ok(m, B, P, n_out));
   if (!outs) { set_error("encoder2: outs is NULL"); return ORCA_B200_EINVAL; }
   ORCA_TRY(check_ptr_device(x, "encoder2: x"));
@@ -1074,6 +1106,7 @@ static int decoder_args_ok(const orca_b200_module* m, int64_t B, int64_t S) {
 }
 
 size_t orca_b200_decoder_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t S) {
+  CallScope scope(m);
   if (decoder_args_ok(m, B, S) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
   decoder_run(m, nullptr, B, S, 0, 0, 0, Plane4(), Plane4(), nullptr, ar, nullptr);
@@ -1084,6 +1117,7 @@ int orca_b200_decoder_forward(const orca_b200_module* m, const float* x, int64_t
                               int64_t xsL, const float* distenc, int64_t dsB, int64_t dsC, int64_t dsH, int64_t dsW,
                               const float* y, int64_t ysB, int64_t ysC, int64_t ysH, int64_t ysW, float* out,
                               void* workspace, size_t workspace_bytes, void* stream) {
+  CallScope scope(m);
   ORCA_TRY(decoder_args_ok(m, B, S));
   ORCA_TRY(check_ptr_device(x, "decoder: x"));
   ORCA_TRY(check_ptr_device(out, "decoder: out"));
@@ -1112,6 +1146,7 @@ static int net_args_ok(const orca_b200_module* m, int64_t B, int64_t L) {
 }
 
 size_t orca_b200_net_workspace_bytes(const orca_b200_module* m, int64_t B, int64_t L) {
+  CallScope scope(m);
   if (net_args_ok(m, B, L) != ORCA_B200_OK) return 0;
   Arena ar; ar.dry = true;
   float dummy;
@@ -1132,6 +1167,7 @@ static int net_forward_common(const orca_b200_module* m, const SeqIn& in, int64_
 
 int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, int64_t L, int64_t sB, int64_t sC,
                           int64_t sL, float* out, float* out_1d, void* workspace, size_t workspace_bytes, void* stream) {
+  CallScope scope(m);
   SeqIn in;
   in.x = x; in.sB = sB; in.sC = sC; in.sL = sL;
   return net_forward_common(m, in, B, L, out, out_1d, workspace, workspace_bytes, stream);
@@ -1140,6 +1176,7 @@ int orca_b200_net_forward(const orca_b200_module* m, const float* x, int64_t B, 
 int orca_b200_net_forward_packed(const orca_b200_module* m, const uint8_t* bases, int64_t B, int64_t L, int64_t sB,
                                  int64_t sL, int32_t complement, float* out, float* out_1d, void* workspace,
                                  size_t workspace_bytes, void* stream) {
+  CallScope scope(m);
   if (sL == 0) { set_error("net_forward_packed: position stride is 0"); return ORCA_B200_EINVAL; }
   SeqIn in;
   in.bases = bases; in.sB = sB; in.sL = sL; in.complement = complement ? 1 : 0;

@@ -1,5 +1,5 @@
 // Tensor-core (tcgen05) path: chunk-plane activations and the conv entry points
-// (conv_tc.cu: Conv1d k=9; conv2d_tc.cu: dilated 3x3 Conv2d).
+// (conv_tc.cu: Conv1d k=9).  The dilated 3x3 Conv2d path of the decoders lives in dec_stream.h / conv2d_stream.cu.
 #pragma once
 #include <vector>
 #include "common.h"
@@ -16,6 +16,9 @@ struct TcAct {
   int nb = 0, C = 0;
   int64_t n = 0, npad = 0;
   int fmt = 0;
+  // fmt 1 only: device word that kernels OR 1 into when a value they round to fp16 exceeds the fp16 range guard
+  // (|x| > 60000); nullptr = no check.  Read through orca_b200_module_status (modules.cu).
+  unsigned int* sat = nullptr;
 };
 
 inline int64_t tc_npad(int64_t n) { return ((n + 127) / 128) * 128 + 8; }
@@ -41,43 +44,7 @@ int tc_pack_lconv1(ConvLayer& L0, const float* w1, const float* b1, const float*
 int tc_lconv1(const ConvLayer& L0, const ConvLayer& L1, const SeqIn& in, int nb, int64_t Ltot, int64_t l_begin, int64_t n,
               TcAct* out, cudaStream_t s);
 
-// ---- 2D: (nb, C, S, S) map as hi/lo[nb][C/8][plane_rows][8]; pixel (y, x) at row y*Wp + 64 + x with
-// Wp = S + 128 (64 zero pixels on each side of every image row); pad pixels must stay zero.
-struct TcMap {
-  void* hi = nullptr;
-  void* lo = nullptr;
-  int nb = 0, C = 0, S = 0, Wp = 0;
-  int64_t plane_rows = 0;
-};
-inline int64_t tc2d_plane_rows(int S) { return (int64_t)S * (S + 128) + 384; }
-inline size_t tc2d_plane_bytes(int nb, int C, int S) { return (size_t)nb * (C / 8) * tc2d_plane_rows(S) * 16; }  // one of hi/lo
-
-bool tc_layer2d_eligible(const ConvLayer& L);
-int tc_pack_layer2d(ConvLayer& L, const float* w_folded /*[tap][c_in][c_out]*/, std::vector<void*>& allocs);
-int tc_conv2d(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu, cudaStream_t s);
-int tc_outer_sum(const float* xcl /*[nb][S][C]*/, TcMap* out, cudaStream_t s);
-int tc_extra_conv(const float* src, int64_t sB, int64_t sC, int64_t sH, int64_t sW, int n_extra, const float* w_extra,
-                  TcMap* out, int mode, cudaStream_t s);
-int tc_final_head_tmp(const TcMap& in, const ConvLayer& f0, const ConvLayer& f1, float* tmp /*[nb][O][S][S]*/, cudaStream_t s);
-
-// All the 3x3 convs of one decoder call as ONE persistent kernel with grid barriers between layers
-// (conv2d_prog.cu).  add() records a layer, run() uploads the layer table into `scratch` and launches.
-class Tc2dProgram {
- public:
-  Tc2dProgram();
-  ~Tc2dProgram();
-  Tc2dProgram(const Tc2dProgram&) = delete;
-  Tc2dProgram& operator=(const Tc2dProgram&) = delete;
-  int add(const ConvLayer& L, const TcMap& in, const TcMap* res, TcMap* out, int relu);
-  int run(void* scratch, size_t scratch_bytes, cudaStream_t s);
-  int size() const;
-  double flop() const;
-  static size_t scratch_bytes(int max_layers);
-
- private:
-  struct Impl;
-  Impl* impl;
-};
+// 2D maps and the decoder kernels: dec_stream.h
 
 // glue.cu
 int symmetrise(const float* tmp, float* out, int B, int S, cudaStream_t s);

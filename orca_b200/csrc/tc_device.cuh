@@ -102,6 +102,16 @@ __device__ __forceinline__ void store_h8(const float* v, void* dst) {
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
 }
+// fp16 range guard of the single-pass stages: flag (never clamp) anything that would round to +-inf or sits within 10 %
+// of the fp16 maximum (65504).  NaN cannot appear before an overflow has been flagged at its source layer.
+template <int N>
+__device__ __forceinline__ void guard_h(const float* v, unsigned int* sat) {
+  if (!sat) return;
+  float m = 0.f;
+#pragma unroll
+  for (int j = 0; j < N; ++j) m = fmaxf(m, fabsf(v[j]));
+  if (!(m <= 60000.f)) atomicOr(sat, 1u);
+}
 __device__ __forceinline__ void add_h8(float* v, const void* src) {
   const uint4 h = __ldg(reinterpret_cast<const uint4*>(src));
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w};

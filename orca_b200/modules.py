@@ -113,6 +113,9 @@ class _NativeModule(nn.Module):
         self._handle = None
         self._handle_device = None
         self._handle_version = None
+        self._handle_options = None
+        # per-module overrides of the process defaults in orca_b200._lib (keys: "impl", "encoder_fp16_stages")
+        self.options = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # -- to be provided by subclasses --------------------------------------------------
@@ -154,6 +157,10 @@ class _NativeModule(nn.Module):
         """Fold + pack + upload the weights on first use (or after they changed)."""
         version = self._param_version()
         if self._handle is not None and self._handle_device == device and self._handle_version == version:
+            stamp = (_lib.options_epoch, tuple(sorted(self.options.items())))
+            if stamp != self._handle_options:  # kernel selection / precision are per handle in the C library
+                _lib.apply_options(self._handle, self.options)
+                self._handle_options = stamp
             return self._handle
         self._invalidate()
         entries = []
@@ -183,7 +190,25 @@ class _NativeModule(nn.Module):
             _lib.check(_lib.lib().orca_b200_module_create(self._kind, arr, len(entries), self._flags(),
                                                           self._num_1d(), ctypes.byref(handle)))
         self._handle, self._handle_device, self._handle_version = handle, device, version
+        _lib.apply_options(handle, self.options)
+        self._handle_options = (_lib.options_epoch, tuple(sorted(self.options.items())))
         return handle
+
+    # -- fp16 range guard (modules with encoder stages) -------------------------------------
+    def fp16_guard_fired(self, clear=True):
+        """True if a single-pass fp16 encoder stage of this module produced a value beyond the fp16 range guard since
+        the last check (orca_b200_module_status; synchronises the device)."""
+        if self._handle is None:
+            return False
+        with torch.cuda.device(self._handle_device):
+            return bool(_lib.module_status(self._handle, clear) & _lib.STATUS_FP16_RANGE)
+
+    def _fall_back_to_fp32_grade(self):
+        import warnings
+        warnings.warn("orca_b200: an activation of %s exceeded the fp16 range in a single-pass encoder stage; this module "
+                      "now runs every stage in the three-product fp32-grade format (encoder_fp16_stages = 0)"
+                      % type(self).__name__, RuntimeWarning, stacklevel=3)
+        self.options["encoder_fp16_stages"] = 0
 
 
 def _require_cuda(name, t, dtypes=(torch.float32,)):
@@ -225,8 +250,12 @@ class Encoder(_NativeModule):
             out += [getattr(self, "lconv%d" % k), getattr(self, "conv%d" % k)]
         return out
 
-    def forward(self, x, bin_range=None, out=None, reverse_complement=False, window=None):
+    def forward(self, x, bin_range=None, out=None, reverse_complement=False, window=None, guard=True):
         """Reference call: forward(x).  Extensions used by orca_b200.predict / orca_b200.parallel:
+
+        guard=True checks the fp16 range guard after the call (one device synchronisation) and, if it fired, reruns
+            the call with every stage in the fp32-grade format and keeps this module there.  The batched drivers pass
+            guard=False and check once per pass (predict.check_fp16_guard) so that nothing synchronises mid-pass.
 
         reverse_complement=True encodes the opposite strand straight from the same buffer:
             RC(x)[b, c, l] = x[b, 3-c, L-1-l] (orca_predict.py:324-329) is x walked with negated strides.
@@ -236,6 +265,14 @@ class Encoder(_NativeModule):
             sequence of L_total bp (a shard uploads its slice plus the 112 kb halo, not the whole input).
         x may also be PACKED bases: a uint8 (B, L) tensor of codes 0..4 / raw ASCII (orca_b200.feeder), 1 B/bp.
         """
+        res = self._forward(x, bin_range, out, reverse_complement, window)
+        if guard and self.fp16_guard_fired():
+            self._fall_back_to_fp32_grade()
+            res = self._forward(x, bin_range, out, reverse_complement, window)
+        return res
+
+    def _forward(self, x, bin_range=None, out=None, reverse_complement=False, window=None):
+        """One native Encoder call; see forward."""
         _require_cuda("Encoder.forward", x, (torch.float32, torch.uint8))
         packed = x.dtype == torch.uint8
         n = x.size(-1)
@@ -460,8 +497,16 @@ class Net(_NativeModule):
     def _num_1d(self):
         return int(self.num_1d) if self.num_1d else 0
 
-    def forward(self, x):
-        """x: float32 (B, 4, L) as the reference takes it, or packed uint8 (B, L) bases (orca_b200.feeder)."""
+    def forward(self, x, guard=True):
+        """x: float32 (B, 4, L) as the reference takes it, or packed uint8 (B, L) bases (orca_b200.feeder).
+        guard: see Encoder.forward (screening loops pass guard=False and call fp16_guard_fired() once per batch)."""
+        res = self._forward(x)
+        if guard and self.fp16_guard_fired():
+            self._fall_back_to_fp32_grade()
+            res = self._forward(x)
+        return res
+
+    def _forward(self, x):
         _require_cuda("Net.forward", x, (torch.float32, torch.uint8))
         packed = x.dtype == torch.uint8
         if (x.dim() != 2 if packed else (x.dim() != 3 or x.size(1) != 4)) or x.size(-1) % 4000 != 0 or x.size(-1) == 0:

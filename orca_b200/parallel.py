@@ -52,9 +52,9 @@ class ShardedForward:
         self._cuts = [self.b0, self.b1]
         self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
-        # how a single GPU runs the two strand cascades: "streams" = four independent chains (2 cascades + 2
-        # Decoder_1m terms) on four CUDA streams, one launch per conv; "batch" = the two strands as the two batch
-        # elements of ONE chain (every decoder call is one persistent program kernel at batch 2)
+        # how a single GPU runs the two strand cascades: "batch" = the two strands as the two batch elements of ONE
+        # chain (every decoder call is one persistent stream kernel at batch 2); "serial" = one strand after the other
+        # at batch 1, which is what each cascade rank of a multi-GPU run does
         self.cascade_mode = "batch"
         self.h2d_bytes = 0
         # maps per level: 1, or num_2d for the multi-dataset shells of orca_leukemia.py
@@ -113,6 +113,8 @@ class ShardedForward:
         enc = torch.empty((1, self.P, 128), dtype=torch.float32, device=self.device)
         bins = (self.P - self.b1, self.P - self.b0) if reverse else (self.b0, self.b1)
         kw = dict(out=enc, reverse_complement=reverse, window=(self.s0, self.L))
+        if hasattr(self.shell.net0, "fp16_guard_fired"):
+            kw["guard"] = False  # native Encoder: the fp16 range guard is checked once per pass, see fp16_guard()
         x = self.window if self.window.dtype == torch.uint8 else self.window.transpose(1, 2)
         ready, self._ready = (self._ready, None) if not reverse else (None, self._ready)
         if ready is not None and len(ready) > 1:  # first use after a staged upload (forward strand)
@@ -127,6 +129,12 @@ class ShardedForward:
                 self._ready = None
             self.shell.net0(x, bin_range=bins, **kw)
         return enc
+
+    def fp16_guard(self):
+        """Call after the maps of a forward() have been read back: True if this rank's encoder tripped its fp16 range
+        guard (it then runs fp32-grade from now on and the forward must be repeated -- on EVERY rank, so callers
+        all-reduce the flag when world > 1)."""
+        return predict.check_fp16_guard([self.shell])
 
     def _gather(self, enc, reverse):
         P, n = self.P, self.b1 - self.b0
@@ -217,11 +225,8 @@ class ShardedForward:
                 if has_1m and rank == x_rank[rev]:
                     finest(rev)
                     jobs.append(("x", rev))
-            # independent chains on separate CUDA streams: each decoder conv is a ~20 us launch whose prologue/tail
-            # latency the other streams' kernels fill (a single chain runs as one persistent program kernel instead)
-            outs = predict.run_concurrent(
-                [(lambda r=r: cascade(r)) if kind == "c" else (lambda r=r: predict.level1_extra(shell, finest(r), mpos, wpos, r)[0])
-                 for kind, r in jobs], self.device)
+            # every decoder call is one persistent kernel that owns all SMs: this rank's chains run back to back
+            outs = [cascade(r) if kind == "c" else predict.level1_extra(shell, finest(r), mpos, wpos, r)[0] for kind, r in jobs]
             for (kind, rev), o in zip(jobs, outs):
                 (preds if kind == "c" else extras)[rev] = o
             if world > 1:  # collect on rank 0: the reverse cascade, and the Decoder_1m terms computed elsewhere

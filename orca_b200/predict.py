@@ -148,7 +148,21 @@ def run_concurrent(jobs, device):
 def encode_strand(model, seq_dev, reverse):
     """net0 on one strand of the uploaded tensor: float32 (B, L, 4) or packed uint8 (B, L)."""
     x = seq_dev if seq_dev.dtype == torch.uint8 else seq_dev.transpose(1, 2)
+    if hasattr(model.net0, "fp16_guard_fired"):  # native Encoder: the range guard is checked once per pass (check_fp16_guard)
+        return model.net0(x, reverse_complement=reverse, guard=False)
     return model.net0(x, reverse_complement=reverse)
+
+
+def check_fp16_guard(models):
+    """After a pass has been read back (the device is idle anyway): did any native encoder trip its fp16 range guard?
+    Such encoders are switched to the fp32-grade format; returns True when the pass has to be repeated."""
+    fired = False
+    for m in models:
+        net0 = getattr(m, "net0", None)
+        if hasattr(net0, "fp16_guard_fired") and net0.fp16_guard_fired():
+            net0._fall_back_to_fp32_grade()
+            fired = True
+    return fired
 
 
 def cascade_starts_32mb(mpos, wpos, reverse):
@@ -274,10 +288,13 @@ def _genomepredict_on(device, sequence, mchr, mpos, wpos, models):
     drives it on the CPU with stand-in networks against fixtures from the unmodified reference driver)."""
     with torch.no_grad():
         seq_dev = _to_device_sequence(sequence, device)
-        results = [_strand_lanes_32mb(model, seq_dev, mpos, wpos) for model in models]
-        stacked = [torch.stack(avg) for avg, _ in results]
-        starts0 = results[0][1]
-        host = [s.cpu().numpy() for s in stacked]
+        for attempt in range(2):
+            results = [_strand_lanes_32mb(model, seq_dev, mpos, wpos) for model in models]
+            stacked = [torch.stack(avg) for avg, _ in results]
+            starts0 = results[0][1]
+            host = [s.cpu().numpy() for s in stacked]
+            if not check_fp16_guard(models):  # else: the encoders now run fp32-grade; repeat the pass once
+                break
     output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
     output["start_coords"] = [wpos - 16000000 + s * 4000 for s in starts0]
     output["end_coords"] = [int(output["start_coords"][ii] + 32000000 / 2 ** ii) for ii in range(6)]
@@ -399,20 +416,23 @@ def _genomepredict_256mb_on(device, sequence, mchr, normmats, chrlen, mpos, wpos
         seq_dev = _to_device_sequence(sequence, device)
         B = seq_dev.shape[0]
         nm_dev = [prepare_background(nm, device) for nm in normmats]
-        per_strand, allns, starts0 = [], [], None
-        for reverse in (False, True):
-            for ii, model in enumerate(models):
-                enc4k = encode_strand(model, seq_dev, reverse)
-                enc128k = model.net1(enc4k, coarsest_only=True)[-1]
-                encs = dict(zip([32, 64, 128, 256], model.net(enc128k)))
-                preds, starts, ns = cascade_256mb(model, encs, B, nm_dev[ii], chrlen, mpos, wpos, reverse)
-                per_strand.append(preds)
-                allns.append(ns)
-                if not reverse and starts0 is None:
-                    starts0 = starts
-        n = len(models)
-        host = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])).cpu().numpy() for i in range(n)]
-        ns_host = [{lvl: t.cpu().numpy() for lvl, t in ns.items()} for ns in allns]
+        for attempt in range(2):
+            per_strand, allns, starts0 = [], [], None
+            for reverse in (False, True):
+                for ii, model in enumerate(models):
+                    enc4k = encode_strand(model, seq_dev, reverse)
+                    enc128k = model.net1(enc4k, coarsest_only=True)[-1]
+                    encs = dict(zip([32, 64, 128, 256], model.net(enc128k)))
+                    preds, starts, ns = cascade_256mb(model, encs, B, nm_dev[ii], chrlen, mpos, wpos, reverse)
+                    per_strand.append(preds)
+                    allns.append(ns)
+                    if not reverse and starts0 is None:
+                        starts0 = starts
+            n = len(models)
+            host = [torch.stack(_average_strands(per_strand[i], per_strand[i + n])).cpu().numpy() for i in range(n)]
+            ns_host = [{lvl: t.cpu().numpy() for lvl, t in ns.items()} for ns in allns]
+            if not check_fp16_guard(models):
+                break
     output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
     output["start_coords"] = [wpos - 128000000 + s * 32000 for s in starts0]
     output["end_coords"] = [np.fmin(int(output["start_coords"][ii] + 256000000 / 2 ** ii), chrlen) for ii in range(4)]

@@ -348,13 +348,13 @@ static void fused_vs_layerwise(int nb, int S) {
   for (auto& m : bufs) CK(cudaFree(m.p));
 }
 
-static void timing(int nb) {
+static void timing(int nb, int fixed_d = 0) {
   std::mt19937 rng(7);
   std::vector<int> dils;
   const int base[7] = {1, 2, 4, 8, 16, 32, 64};
-  for (int r = 0; r < 4; ++r) for (int i = 0; i < 7; ++i) dils.push_back(base[i]);
+  for (int r = 0; r < 4; ++r) for (int i = 0; i < 7; ++i) dils.push_back(fixed_d ? fixed_d : base[i]);
   dils.erase(dils.begin());  // 27 units after the combiner stage (Decoder.forward with a coarse input)
-  Program P = build_program(dils, true, rng);
+  Program P = build_program(dils, fixed_d == 0, rng);
   const int S = 250;
   auto x = random_map(nb, 64, S, rng);
   DMap bufs[6];
@@ -364,6 +364,7 @@ static void timing(int nb) {
   const float ms = run_program(P, bufs, true, 10);
   double flop = 0;
   for (auto& h : P.layers) flop += 2.0 * nb * S * S * 9.0 * h.L.c_in * h.L.c_out;
+  if (fixed_d) printf("(all units at d = %d, no combiner layers) ", fixed_d);
   printf("timing: %zu-layer Decoder-shaped program, batch %d, S=250: %.3f ms per launch, %.1f algorithmic TFLOP/s (x3 issued: %.1f)\n",
          P.layers.size(), nb, ms, flop / ms * 1e-9, 3 * flop / ms * 1e-9);
   for (auto& m : bufs) CK(cudaFree(m.p));
@@ -371,12 +372,16 @@ static void timing(int nb) {
 
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strncmp(argv[1], "time", 4)) {  // "time1" / "time2": only the Decoder-shaped timing run (ncu target)
+    timing(argv[1][4] == '1' ? 1 : 2);
+    return 0;
+  }
   OK(ds_debug_enable(1));
   single_layer_tests();
   check_stall("single-layer tests");
   fused_vs_layerwise(1, 64);
   fused_vs_layerwise(2, 250);
-  if (!quick) { timing(1); timing(2); }
+  if (!quick) { timing(1); timing(2); timing(2, 1); timing(2, 8); timing(2, 64); timing(1, 1); timing(1, 64); }
   printf("%s (%d failures)\n", n_fail ? "FAILED" : "ALL PASS", n_fail);
   return n_fail ? 1 : 0;
 }

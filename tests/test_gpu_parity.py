@@ -5,12 +5,13 @@ Bar (BASELINE.json north star): max|ours - ref| / max|ref| <= 1e-3 per output, f
 The fp32 SIMT path is additionally held to 5e-5 (it differs from the reference only by fp32
 summation order and the BatchNorm fold)."""
 import os
+import sys
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, relerr
+from conftest import GOLDEN, ROOT, relerr
 import orca_oracle as oracle
 from orca_b200 import _lib, modules, synthetic
 
@@ -304,11 +305,12 @@ def test_genomepredict_32mb_golden():
     runner.upload(torch.from_numpy(seq))
     maps = runner.forward(mpos, wpos).cpu().numpy()
     assert max(relerr(maps[i], g["predictions"][i]) for i in range(6)) <= TOL
-    # the four-stream schedule (one launch per conv) computes the same maps as the batched-strand chain
-    runner.cascade_mode = "streams"
+    # one strand cascade at a time (what a multi-GPU rank runs) computes bit-identical maps to the batched-strand chain:
+    # the arithmetic of a tile does not depend on the batch or on the schedule
+    runner.cascade_mode = "serial"
     maps_s = runner.forward(mpos, wpos).cpu().numpy()
     runner.cascade_mode = "batch"
-    assert max(relerr(maps_s[i], maps[i]) for i in range(6)) <= 1e-4  # same arithmetic, different summation order of the row taps
+    assert np.array_equal(maps_s, maps)
     # packed-base feeder (1 B/bp): identical maps from both drivers
     from orca_b200 import feeder
     codes = feeder.from_onehot(seq)
@@ -409,6 +411,171 @@ def test_sharded_runner_256mb_matches_driver():
     assert maps.shape == (4, 250, 250) and np.isfinite(maps).all()
     for i in range(4):
         assert relerr(maps[i], ref["predictions"][0][i]) <= 1e-6, i
-    runner.cascade_mode = "streams"
+    runner.cascade_mode = "serial"
     maps_s = runner.forward(mpos, wpos).cpu().numpy()
-    assert max(relerr(maps_s[i], maps[i]) for i in range(4)) <= 1e-4
+    assert np.array_equal(maps_s, maps)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: batch 4, full-size Orca-1Mb, hard cases for the single-pass fp16 stages, HCTnoc shell, strand-dependent
+# 256 Mb stub, and the UNMODIFIED reference drivers on native shells
+# ---------------------------------------------------------------------------------------------------
+def test_batch4_golden():
+    g = gold("encoder_b4_24k")
+    m = native(modules.Encoder(), int(g["weight_seed"]))
+    seq = synthetic.random_sequence(4, int(g["L"]), int(g["seq_seed"]), float(g["n_fraction"]))
+    y = m(torch.from_numpy(seq).transpose(1, 2).cuda())
+    assert relerr(y.cpu().numpy(), g["out"]) <= TOL
+    g = gold("decoder_b4_40")
+    d = native(modules.Decoder(upsample_mode="bilinear"), int(g["weight_seed"]))
+    x = randn((4, 128, 40), int(g["x_seed"]), 0.5).cuda()
+    distenc, yc = randn((4, 1, 40, 40), int(g["d_seed"])).cuda(), randn((4, 1, 20, 20), int(g["y_seed"])).cuda()
+    y = d(x, distenc, yc)
+    assert relerr(y.cpu().numpy(), g["out"]) <= TOL
+    for b in range(4):  # a batch element does not depend on its neighbours
+        assert torch.equal(d(x[b:b + 1], distenc[b:b + 1], yc[b:b + 1]), y[b:b + 1])
+
+
+def test_net_1mb_golden():
+    """Orca-1Mb at full size (README.md:204-219 screen path): Net.forward on 1 Mb vs the reference class."""
+    g = gold("net_1mb")
+    m = native(modules.Net(num_1d=32), int(g["weight_seed"]))
+    seq = synthetic.random_sequence(1, 1_000_000, int(g["seq_seed"]), float(g["n_fraction"]))
+    pred, p1d = m(torch.from_numpy(seq).transpose(1, 2).cuda())
+    e2, e1 = relerr(pred.cpu().numpy(), g["out"]), relerr(p1d.cpu().numpy(), g["out_1d"])
+    print("net_1mb relerr 2d %.2e 1d %.2e" % (e2, e1))
+    assert e2 <= TOL and e1 <= TOL
+
+
+@pytest.mark.parametrize("name", ["encoder_hard_alln", "encoder_hard_homopolymer", "encoder_hard_nruns", "encoder_hard_widebn",
+                                  "encoder_hard_heavytail"])
+def test_fp16_stages_on_hard_inputs(name):
+    """the single-pass fp16 stages on inputs / weights that stress them -- all-N, homopolymer, long N
+    runs, BatchNorm scales in [0.1, 10] (activations reach 1e7: beyond fp16), heavy-tailed conv weights -- against the
+    reference.  At the DEFAULT setting every case must meet the 1e-3 bar; where the fp16 range is exceeded the range
+    guard must fire and the module must fall back to the fp32-grade format by itself."""
+    g = gold(name)
+    m = modules.Encoder()
+    m.load_state_dict(synthetic.fill_state_dict(m.state_dict(), int(g["weight_seed"]), recipe=str(g["recipe"])))
+    m = m.eval().cuda()
+    seq = synthetic.hard_sequence(1, int(g["L"]), int(g["seq_seed"]), str(g["seqkind"]))
+    x = torch.from_numpy(seq).transpose(1, 2).cuda()
+    import warnings
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        y = m(x)
+    fell_back = m.options.get("encoder_fp16_stages") == 0
+    e = relerr(y.cpu().numpy(), g["out"])
+    print(name, "relerr %.2e" % e, "| fp16 range guard fired -> fp32-grade fallback" if fell_back else "| single-pass fp16 stages kept")
+    assert np.isfinite(y.cpu().numpy()).all() and e <= TOL
+    assert fell_back == any("fp16 range" in str(i.message) for i in w)
+    if float(np.abs(g["out"]).max()) > 1e5:  # activations far beyond 65504 on the way: the guard has to catch it
+        assert fell_back
+    if not fell_back:  # and the fp32-grade path agrees as well
+        m.options["encoder_fp16_stages"] = 0
+        assert relerr(m(x).cpu().numpy(), g["out"]) <= 5e-5
+    # without the guard the same module at single-pass precision would have been wrong / non-finite for the overflow case
+    if fell_back:
+        m.options["encoder_fp16_stages"] = 3
+        bad = m(x, guard=False).cpu().numpy()
+        assert m.fp16_guard_fired() and (not np.isfinite(bad).all() or relerr(bad, g["out"]) > TOL)
+
+
+def test_genomepredict_32mb_hctnoc_golden():
+    """HCTnoc-like shell end to end (orca_models.py:335-446: Encoder2b, nearest upsampling, no Decoder_1m), zooming into
+    the left edge of the window (crop index clipped to 0).  Fixture: the unmodified driver with a zero Decoder_1m term
+    attached (as written, orca_predict.py:362 raises AttributeError on the reference HCTnoc shell)."""
+    from orca_b200 import models, predict
+    g = gold("genomepredict_32mb_hctnoc")
+    shell = models.HCTnoc(seed=int(g["shell_seed"]))
+    assert not hasattr(shell, "denet_1_pt") and isinstance(shell.net, modules.Encoder2b)
+    seq = synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"]))
+    out = predict.genomepredict(seq, "chrS", int(g["mpos"]), int(g["wpos"]), models=[shell])
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("genomepredict 32 Mb HCTnoc-like relerr per level (32..1 Mb):", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
+
+
+def test_genomepredict_256mb_strand_dependent_stub():
+    """genomepredict_256Mb with a stub net0 that depends on its input (the two strands differ), a chromosome shorter than
+    the window, an off-centre zoom; also checks end_coords and the float64 block-mean backgrounds it returns."""
+    from orca_b200 import models, predict
+    g = gold("genomepredict_256mb_stub2")
+    shell = models.H1esc_256M(seed=int(g["shell_seed"]))
+
+    class StubNet0(torch.nn.Module):
+        def forward(self, x, reverse_complement=False):
+            if reverse_complement:
+                x = x.flip(1).flip(2)
+            w = torch.from_numpy(np.random.default_rng(int(g["w_seed"])).standard_normal((128, 4)).astype(np.float32)).to(x.device)
+            e = torch.einsum("kc,bcl->bkl", w, x)
+            return 0.5 * (e + 0.5 * torch.roll(e, 1, 2) + 0.25 * torch.roll(e, -3, 2))
+    shell.net0 = StubNet0()
+    seq = synthetic.random_sequence(1, 64000, int(g["seq_seed"]), 0.01)
+    nm = synthetic.normmat_256mb(chrlen_bins=int(g["chrlen_bins"]))
+    out = predict.genomepredict_256Mb(seq, "chrS", [nm], int(g["chrlen"]), int(g["mpos"]), int(g["wpos"]), models=[shell])
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    assert [int(v) for v in out["end_coords"]] == [int(v) for v in g["end_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("genomepredict 256 Mb (strand-dependent stub) relerr per level:", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
+    nms = np.stack([np.stack([ns[l][0] for l in (256, 128, 64, 32)]) for ns in out["normmats"]])
+    assert nms.dtype == np.float64 and nms.shape == g["normmats"].shape
+    assert np.allclose(nms, g["normmats"], rtol=1e-12, atol=0)
+
+
+def _reference_tree():
+    """The reference sources as TEST DATA: /root/reference in the build container, or the git-ignored payload copy that
+    tools/ship_reference.sh places under tests/_reference_payload/ for a gpurun call (never committed)."""
+    for p in (os.environ.get("ORCA_REFERENCE"), "/root/reference", os.path.join(ROOT, "tests", "_reference_payload")):
+        if p and os.path.isfile(os.path.join(p, "orca_predict.py")):
+            return p
+    return None
+
+
+@pytest.mark.skipif(_reference_tree() is None, reason="reference sources not available on this box")
+def test_unmodified_reference_drivers_on_native_shells():
+    """The drop-in promise of INTEGRATION.md section 1: the UNMODIFIED orca_predict.genomepredict /
+    genomepredict_256Mb, imported from the reference tree, driven with native shells (models=[shell], use_cuda=True),
+    against the fixtures the same drivers produced on the reference's own modules."""
+    import types
+    ref = _reference_tree()
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    for name, attrs in {"selene_utils2": ["MemmapGenome", "Genomic2DFeatures"], "selene_sdk": [], "selene_sdk.sequences": ["Genome"],
+                        "orca_utils": ["genomeplot", "genomeplot_256Mb", "StructuralChange2", "process_anno", "coord_round", "coord_clip"]}.items():
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            for a in attrs:
+                setattr(mod, a, type(a, (), {}))
+            sys.modules[name] = mod
+    sys.modules["selene_sdk"].sequences = sys.modules["selene_sdk.sequences"]
+    import orca_predict
+    from orca_b200 import models
+    g = gold("genomepredict_32mb")
+    shell = models.H1esc(seed=int(g["shell_seed"]))
+    seq = synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"]))
+    n0 = _lib.launch_count()
+    out = orca_predict.genomepredict(seq, "chrS", int(g["mpos"]), int(g["wpos"]), models=[shell], use_cuda=True)
+    assert _lib.launch_count() > n0
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("UNMODIFIED orca_predict.genomepredict on a native H1esc shell: relerr per level", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL
+    # 256 Mb driver with the stub 4 kb encoding of the fixture
+    g = gold("genomepredict_256mb_stub")
+    shell = models.H1esc_256M(seed=int(g["shell_seed"]))
+
+    class StubNet0(torch.nn.Module):
+        def forward(self, x):
+            e = np.random.default_rng(int(g["enc_seed"])).standard_normal((x.shape[0], 128, 64000)) * 0.5
+            return torch.from_numpy(e.astype(np.float32)).cuda()
+    shell.net0 = StubNet0()
+    nm = synthetic.normmat_256mb(chrlen_bins=int(g["chrlen_bins"]))
+    out = orca_predict.genomepredict_256Mb(synthetic.random_sequence(1, 4000, 107), "chrS", [nm], int(g["chrlen"]), int(g["mpos"]),
+                                           int(g["wpos"]), models=[shell], use_cuda=True)
+    assert out["start_coords"] == [int(v) for v in g["start_coords"]]
+    errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
+    print("UNMODIFIED orca_predict.genomepredict_256Mb on a native H1esc_256M shell: relerr per level", ["%.1e" % e for e in errs])
+    assert max(errs) <= TOL

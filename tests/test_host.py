@@ -106,7 +106,7 @@ def test_module_create_validates_architecture():
         p.c_in, p.c_out, p.kh, p.kw, p.dilation = 64, 64, 1, 9, 1
     st = lib.orca_b200_module_create(_lib.ENCODER, arr, 28, 0, 0, ctypes.byref(handle))
     assert st == -1 and b"conv 0" in lib.orca_b200_last_error()
-    assert lib.orca_b200_set_impl(7) == -1
+    assert lib.orca_b200_module_set_option(None, _lib.OPT_IMPL, 1) == -1 and b"NULL module" in lib.orca_b200_last_error()
 
 
 def test_abi_argument_checks_without_a_gpu():
@@ -128,8 +128,11 @@ def test_abi_argument_checks_without_a_gpu():
     assert lib.orca_b200_background_bins(regs, 3, 32000) == -1 and b"empty" in lib.orca_b200_last_error()
     # packed encoder input with a zero position stride is rejected before any pointer is looked at
     assert lib.orca_b200_encoder_forward_packed(None, None, 1, 4000, 4000, 0, 0, 0, 4000, None, 0, 1, 0, None, 0, None) == -1
-    assert lib.orca_b200_set_encoder_fp16_stages(-1) == 3  # default: stages 1-3 single-pass
-    assert lib.orca_b200_set_encoder_fp16_stages(-1) == 3
+    # kernel selection / precision defaults live on the Python side and reach the library per handle
+    assert _lib.set_encoder_fp16_stages(0) == 3  # previous effective setting: library default, stages 1-3 single-pass
+    assert _lib.set_encoder_fp16_stages(-1) == 0
+    with pytest.raises(ValueError):
+        _lib.set_impl("cpu")
 
 
 def test_synthetic_is_deterministic():
