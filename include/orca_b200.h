@@ -109,7 +109,10 @@ const char* orca_b200_last_error(void);
  *       (orca_modules.py:811-927) run their convolutions as ONE fp16 tensor-core product with fp16 activations; the
  *       remaining stages -- and every other module -- keep fp32-grade arithmetic (operands split into two bf16, three
  *       products).  Default 3: stages 1-3 hold 97 % of the encoder FLOP and their 2^-12 rounding noise is averaged out
- *       by stages 4-7.  0 = three products everywhere; -1 restores the default.
+ *       by stages 4-7 -- PROVIDED the folded weights are well conditioned: module_create measures
+ *       the spread of the folded weight row norms of those stages (max / median per conv) and the default drops to 0 when
+ *       it exceeds 4 (BatchNorm scales spanning orders of magnitude).  0 = three products everywhere; -1 restores the
+ *       default; orca_b200_module_get_option returns the effective value.
  * orca_b200_module_status reads (and optionally clears) the handle's device status word; it synchronises the device.
  *   bit 0  ORCA_B200_STATUS_FP16_RANGE: a value written by a single-pass fp16 stage exceeded the fp16 range guard
  *          (|x| > 60000) since the word was last cleared -- the output of that forward is not trustworthy; rerun it

