@@ -2,23 +2,31 @@
 """
 bench.py -- headline benchmark of the Orca forward hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W              # our CUDA path
-    python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host CPU
+    python bench.py --gpus N --steps K --warmup W                  # our CUDA path (default workload: 32mb)
+    python bench.py --impl reference --steps K --warmup W          # the reference algorithm on the host CPU
+    python bench.py --workload {32mb,256mb,batch8,screen} ...      # the other BASELINE.json configs
 
-Workload (BASELINE.json configs[1]): H1esc-like 32 Mb multiscale forward, batch 1, synthetic one-hot
-sequence, random-init weights.  One step = one genomepredict pass of one model: both strands
-(forward + reverse complement) x [Encoder (32 Mb -> 8000 bins) + Encoder2 + 6-level Decoder cascade
-+ Decoder_1m] = 64 Mbp encoded and 12 contact maps decoded (6 after strand averaging).
+Workloads (BASELINE.json `configs`; synthetic one-hot input, random-init weights):
+  32mb    configs[1], the default and what the driver runs: H1esc-like 32 Mb multiscale forward, batch 1.  One step =
+          one genomepredict pass of one model: both strands x [Encoder (32 Mb -> 8000 bins) + Encoder2 + 6-level Decoder
+          cascade + Decoder_1m] = 64 Mbp encoded and 12 contact maps decoded (6 after strand averaging).
+          N > 1: the 8000 4-kb bins are sharded over the ranks (112 kb halo recompute), the encodings are all-gathered
+          over NCCL, the strand cascades run on different ranks.
+  256mb   configs[3]: H1esc_256M-like genomepredict_256Mb forward (256 Mb, 4 levels), sequence-sharded the same way.
+  batch8  configs[2]: Hff-like shell, 8 distinct 32 Mb sequences, both strands, modules called directly (genomepredict
+          keeps batch element 0 only, orca_predict.py:516); N > 1: data parallel over the sequences.
+  screen  configs[4]: in-silico screen, 4096 x 1 Mb windows sliding along a 65 Mb synthetic chromosome through Encoder +
+          level-1 Decoder + Decoder_1m, micro-batched; N > 1: data parallel over the windows, maps gathered on rank 0.
 
-  value   Mbp/s with the sequence already resident in HBM (device-timed, CUDA events)
-  e2e     same metric through orca_b200.predict.genomepredict with the HOST fp32 (1, L, 4) array in
-          pinned memory: the H2D upload and the D2H read of the 6 maps are inside the timed region
-  N > 1   the 8000 4-kb bins are sharded over the ranks (112 kb halo recompute), the encodings are
-          all-gathered over NCCL, strand cascades run on different ranks ("scaling": "strong")
+  value   the metric with the input already resident in HBM (device-timed, CUDA events)
+  e2e     the same metric through the public API with HOST input: the H2D upload and the D2H read of the maps are inside
+          the timed region (N = 1, 32mb / 256mb: orca_b200.predict.genomepredict* on a pinned array, and beside it on a
+          pageable numpy array as the reference's callers hand it over; N > 1: orca_b200.parallel.ShardedForward)
 """
 import argparse
 import json
 import os
+import platform
 import subprocess
 import sys
 import threading
@@ -35,6 +43,7 @@ METRIC = "Mbp/s encoded (32 Mb genomepredict forward, both strands; contact maps
 FLOP_PER_BP_ENCODER = 465_555.4       # SURVEY.md 8d (monolithic-convolution definition)
 FLOP_PER_STRAND = 16.84e12            # Encoder 14.898 + Encoder2 0.0274 + decoders 1.911 TFLOP
 MAPS_PER_STEP = 12                    # raw decoder maps per step (6 levels x 2 strands)
+FLOP_PER_WINDOW = 0.4656e12 + 0.2812e12 + 0.1775e12   # screen: Encoder 1 Mb + Decoder (no coarse) + Decoder_1m
 
 
 def load_peaks():
@@ -48,6 +57,16 @@ def load_peaks():
                 "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", burst)), "source": "measured"}
     except (OSError, ValueError, KeyError, TypeError):
         return fallback
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or "unknown"
 
 
 class ClockSampler(threading.Thread):
@@ -95,14 +114,21 @@ CPU_SAMPLE = ("%d of 40 encoder blocks per strand (912 kb each incl. the 112 kb 
               "Decoder_1m" % (CPU_BLOCKS, CPU_DECODERS))
 
 
+def _oracle():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import orca_oracle as oracle
+    return oracle
+
+
 def cpu_sample(threads):
     """Time a bounded sample (~10-20 s of CPU work on a 16-core host) of the workload with the oracle port on `threads` host threads
     and extrapolate to one full step.  Sample: CPU_BLOCKS 800 kb encoder blocks with their 112 kb halo
     (orca_modules.py:957-977), Encoder2 on 8000 bins, CPU_DECODERS Decoder calls and one Decoder_1m call; returns
     per-unit seconds (block, Encoder2, Decoder, Decoder_1m)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import orca_oracle as oracle
+    oracle = _oracle()
     from orca_b200 import modules, synthetic
     torch.set_num_threads(threads)
     sd_e = synthetic.fill_state_dict(modules.Encoder().state_dict(), 0)
@@ -130,16 +156,41 @@ def cpu_sample(threads):
     return one
 
 
-def cpu_extrapolate(t_block, t_enc2, t_dec, t_d1m):
-    """Seconds for one full step (2 strands) from the sample timings: 40 blocks of 800 kb per strand."""
-    per_strand = 40 * t_block + t_enc2 + 6 * t_dec + t_d1m
-    return 2 * per_strand
+def cpu_full_seconds(workload, tb, te, td, tm, n_units):
+    """Seconds of the reference CPU path for one full step of `workload`, extrapolated linearly from the per-unit sample
+    timings (tb = one 912 kb encoder block, te = Encoder2 @ 8000 bins, td = one Decoder call, tm = one Decoder_1m call)."""
+    per_strand_32 = 40 * tb + te + 6 * td + tm
+    if workload == "32mb":
+        return 2 * per_strand_32
+    if workload == "256mb":  # 320 blocks, pooling half of Encoder2 at 64000 bins (8 x 1/3 of the 8000-bin U-net), 4 decoders
+        return 2 * (320 * tb + 8 * te / 3 + 4 * td)
+    if workload == "batch8":
+        return 8 * 2 * per_strand_32
+    if workload == "screen":  # a 1 Mb window = 1000/912 blocks' worth of encoder + Decoder + Decoder_1m
+        return n_units * (tb * 1000.0 / 912.0 + td + tm)
+    raise ValueError(workload)
+
+
+def workload_units(args):
+    """(label, bp encoded per step, raw maps per step, algorithmic FLOP per step)."""
+    if args.workload == "32mb":
+        return ("H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])", 2 * args.seq_len, MAPS_PER_STEP,
+                2 * FLOP_PER_STRAND * (args.seq_len / SEQ_LEN))
+    if args.workload == "256mb":
+        return ("H1esc_256M-like 256 Mb multiscale forward (genomepredict_256Mb), batch 1 (BASELINE configs[3])", 2 * 256_000_000, 8,
+                2 * 120.6e12)
+    if args.workload == "batch8":
+        return ("Hff-like 32 Mb model, batch of 8 distinct sequences, both strands, modules called directly (BASELINE configs[2])",
+                8 * 2 * SEQ_LEN, 8 * MAPS_PER_STEP, 8 * 2 * FLOP_PER_STRAND)
+    return ("in-silico screen: %d x 1 Mb windows through Encoder + level-1 Decoder + Decoder_1m (BASELINE configs[4])" % args.screen_windows,
+            args.screen_windows * 1_000_000, args.screen_windows, args.screen_windows * FLOP_PER_WINDOW)
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    label, bp_step, maps_step, _ = workload_units(args)
     one = cpu_sample(threads)
     for _ in range(args.warmup):
         one()
@@ -149,19 +200,131 @@ def run_reference(args, rank):
         acc += np.array(one())
     wall = time.perf_counter() - t0
     tb, te, td, tm = acc / args.steps
-    full = cpu_extrapolate(tb, te, td, tm)
-    value = 2 * SEQ_LEN / full / 1e6
-    sample = ("per step: " + CPU_SAMPLE + "; extrapolated linearly to 2 strands x (40 blocks + Encoder2 + 6 Decoder + Decoder_1m)")
+    full = cpu_full_seconds(args.workload, tb, te, td, tm, args.screen_windows)
+    value = bp_step / full / 1e6
+    sample = ("per step: " + CPU_SAMPLE + "; extrapolated linearly to the full step of the workload")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])",
-                       "seq_len": SEQ_LEN, "strands": 2, "models": 1},
-            "contact_maps_per_s": MAPS_PER_STEP / full,
+            "config": {"workload": label, "seq_len": args.seq_len, "strands": 2, "models": 1},
+            "contact_maps_per_s": maps_step / full,
+            "extrapolated": True,
+            "note": "ms_per_step is COMPUTED from the per-unit timings of the bounded sample, not measured; the measured wall "
+                    "time of one sample step is cpu_baseline.sample_wall_s",
             "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": threads, "kind": "port", "sample": sample,
-                             "sample_wall_s": wall / max(args.steps, 1)},
+                             "sample_wall_s": wall / max(args.steps, 1), "extrapolated": True, "cpu": cpu_model(),
+                             "torch_threads": threads},
             "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# the reference GRAPH on the same B200 under eager PyTorch + cuDNN ("the kernel to beat on the same box")
+# ----------------------------------------------------------------------------------------------------
+def gpu_reference(dev, seq_host, mpos, wpos, steps, warmup):
+    """The reference's own GPU path is `.cuda()` + stock torch.nn layers (orca_predict.py:334): its graph restated with
+    torch.nn.functional operators (the oracle port, bit-identical operators) executed on CUDA tensors = eager PyTorch +
+    cuDNN, one full 32 Mb genomepredict-equivalent pass (both strands: blockwise Encoder, Encoder2, 6 Decoders + Decoder_1m
+    each), timed with CUDA events under cuDNN's default TF32 convolutions and with allow_tf32 = False."""
+    import torch
+    oracle = _oracle()
+    from orca_b200 import modules, predict, synthetic
+
+    def sd_of(module, seed):
+        return {k: v.to(dev) for k, v in synthetic.fill_state_dict(module.state_dict(), seed).items()}
+    sd_e, sd_n = sd_of(modules.Encoder(), 0), sd_of(modules.Encoder2(), 1)
+    sd_d = {lvl: sd_of(modules.Decoder(upsample_mode="bilinear"), 10 + i) for i, lvl in enumerate([1, 2, 4, 8, 16, 32])}
+    sd_m = sd_of(modules.Decoder_1m(), 3)
+    mats, _ = synthetic.normmats_32mb()
+
+    class Dec:
+        def __init__(self, sd):
+            self.sd = sd
+
+        def forward(self, x, distenc, y=None):
+            return oracle.decoder_forward(self.sd, x, distenc, y, "bilinear")
+
+    class Dec1m:
+        def forward(self, x):
+            return oracle.decoder_1m_forward(sd_m, x)
+
+    class Shell:
+        pass
+    shell = Shell()
+    shell.normmats = mats
+    shell.denets = {lvl: Dec(sd) for lvl, sd in sd_d.items()}
+    shell.denet_1_pt = Dec1m()
+    seq_dev = seq_host.to(dev)
+
+    def step():
+        with torch.no_grad():
+            outs = []
+            for rev in (False, True):
+                x = (torch.flip(seq_dev, [1, 2]) if rev else seq_dev).transpose(1, 2)  # the reference uploads a flipped copy (:324-329)
+                e = oracle.encoder_forward(sd_e, x)
+                encs = dict(zip([1, 2, 4, 8, 16, 32], oracle.encoder2_forward(sd_n, e)))
+                outs.append(predict.cascade_32mb(shell, encs, 1, mpos, wpos, rev)[0])
+            return [0.5 * f[0] + 0.5 * torch.flip(r[0], [1, 2]) for f, r in zip(*outs)]
+    res = {}
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(warmup):
+                step()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(steps):
+                maps = step()
+            ev1.record()
+            torch.cuda.synchronize()
+            res[tag + "_ms"] = ev0.elapsed_time(ev1) / steps
+            res[tag + "_maps"] = torch.stack([m[0] for m in maps]).cpu().numpy()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    del seq_dev
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_matmul_peaks(dev):
+    """bf16 and TF32 dense peaks measured in this run the way MEASURED_PEAKS.json was (torch.matmul 8192^3, best of 10)."""
+    import torch
+    out = {}
+    n = 8192
+    for tag, dtype, tf32 in (("bf16_tflops", torch.bfloat16, False), ("tf32_tflops", torch.float32, True)):
+        a = torch.randn((n, n), device=dev, dtype=dtype)
+        b = torch.randn((n, n), device=dev, dtype=dtype)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            best = 1e9
+            for i in range(12):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    best = min(best, e0.elapsed_time(e1))
+            out[tag] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
+    torch.cuda.empty_cache()
+    return out
+
+
+def committed_traffic():
+    """DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures
+    (profiles/r02_traffic.json, written by tools/summarise_profiles.py): {label: {dram_bytes, flop, source}}."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -175,15 +338,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--seq-len", type=int, default=SEQ_LEN)
-    ap.add_argument("--workload", default="32mb", choices=["32mb", "256mb"],
-                    help="32mb = BASELINE configs[1] (default, what the driver runs); 256mb = configs[3], the "
-                         "H1esc_256M-like genomepredict_256Mb forward (256 Mb, 4 levels), sequence-sharded the same way")
+    ap.add_argument("--workload", default="32mb", choices=["32mb", "256mb", "batch8", "screen"])
+    ap.add_argument("--screen-windows", type=int, default=4096)
+    ap.add_argument("--micro-batch", type=int, default=8, help="screen: windows per Encoder / Decoder call")
+    ap.add_argument("--verify", action="store_true", help="also check the outputs against a reference fixture / the oracle and "
+                    "put parity_relerr in the line; the run fails if it exceeds 1e-3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--enc-fp16-stages", type=int, default=-1,
                     help="leading encoder stages in single-pass fp16 (0 = three-product bf16 everywhere; default: library default, 3)")
     ap.add_argument("--cascade-mode", default=None, choices=["serial", "batch"])
     ap.add_argument("--chunk-bp", type=int, default=0, help="encoder chunk length in bp (0 = library default)")
-    ap.add_argument("--concurrent-strands", action="store_true", help="encode the two strands on two CUDA streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,27 +373,7 @@ def main():
     if args.enc_fp16_stages >= 0:
         enc16 = min(args.enc_fp16_stages, 7)
     peaks = load_peaks()
-    big = args.workload == "256mb"
-    L = 256_000_000 if big else args.seq_len
-    maps_per_step = 8 if big else MAPS_PER_STEP
-    flop_per_strand = 120.6e12 if big else FLOP_PER_STRAND * (L / SEQ_LEN)
-    workload = ("H1esc_256M-like 256 Mb multiscale forward (genomepredict_256Mb), batch 1 (BASELINE configs[3])" if big
-                else "H1esc-like 32 Mb multiscale forward, batch 1 (BASELINE configs[1])")
-
-    shell = (models.H1esc_256M if big else models.H1esc)(seed=0, device=dev)
-    shell.net0.chunk_bp = args.chunk_bp
-    seq_host = torch.from_numpy(synthetic.random_sequence(1, L, 0)).pin_memory()
-    runner = parallel.ShardedForward(shell, L, rank, world, dev)
-    runner.concurrent_strands = args.concurrent_strands
-    if args.cascade_mode:
-        runner.cascade_mode = args.cascade_mode
-    runner.upload(seq_host)  # device-resident input for the `value` leg
-    if big:
-        runner.set_background(synthetic.normmat_256mb(chrlen_bins=7500), 7500 * 32000)
-        runner.d2h_bytes = 4 * 250 * 250 * 4 if rank == 0 else 0
-        mpos, wpos = 100_000_000, 128_000_000
-    else:
-        mpos = wpos = L // 2
+    label, bp_step, maps_step, flop_step = workload_units(args)
 
     def barrier():
         if world > 1:
@@ -250,13 +395,52 @@ def main():
             ms = float(t.item())
         return ms
 
-    def step_device():
-        return runner.forward(mpos, wpos)
+    parity = None
+    verify_fn = None
+    if args.workload in ("32mb", "256mb"):
+        big = args.workload == "256mb"
+        L = 256_000_000 if big else args.seq_len
+        shell = (models.H1esc_256M if big else models.H1esc)(seed=0, device=dev)
+        shell.net0.chunk_bp = args.chunk_bp
+        seq_np = synthetic.random_sequence(1, L, 0)                 # pageable numpy, as a reference caller holds it
+        seq_host = torch.from_numpy(seq_np).pin_memory()
+        runner = parallel.ShardedForward(shell, L, rank, world, dev)
+        if args.cascade_mode:
+            runner.cascade_mode = args.cascade_mode
+        runner.upload(seq_host)  # device-resident input for the `value` leg
+        if big:
+            nm256 = synthetic.normmat_256mb(chrlen_bins=7500)
+            runner.set_background(nm256, 7500 * 32000)
+            runner.d2h_bytes = 4 * 250 * 250 * 4 if rank == 0 else 0
+            mpos, wpos = 100_000_000, 128_000_000
+        else:
+            mpos = wpos = L // 2
 
-    def step_e2e():
-        runner.upload(seq_host)
-        maps = runner.forward(mpos, wpos)
-        return maps.cpu() if maps is not None else None
+        def step_device():
+            return runner.forward(mpos, wpos)
+
+        def step_e2e_sharded(host):
+            runner.upload(host)
+            maps = runner.forward(mpos, wpos)
+            return maps.cpu() if maps is not None else None
+
+        def step_api(host):  # the public single-process API: orca_b200.predict.genomepredict*
+            if big:
+                return predict.genomepredict_256Mb(host, "chrS", [nm256], 7500 * 32000, mpos, wpos, models=[shell])
+            return predict.genomepredict(host, "chrS", mpos, wpos, models=[shell])
+
+        step_e2e = (lambda: step_api(seq_host)) if world == 1 else (lambda: step_e2e_sharded(seq_host))
+        e2e_api = ("orca_b200.predict.%s (pinned host array)" % ("genomepredict_256Mb" if big else "genomepredict")) if world == 1 \
+            else "orca_b200.parallel.ShardedForward.upload + forward (pinned host array)"
+        h2d_bytes = int(L * 16 if world == 1 else runner.h2d_bytes)
+        d2h_bytes = int(runner.d2h_bytes)
+        config_extra = {"seq_len": L, "strands": 2, "models": 1,
+                        "l2": "inputs (%d MB) and stage activations (>1 GB per chunk) exceed the 126 MB L2" % (L * 16 // 1_000_000),
+                        "parallelism": "sequence-sharded encoder x%d + all-gather, strand-parallel cascades" % world if world > 1 else "single GPU"}
+    elif args.workload == "batch8":
+        step_device, step_e2e, h2d_bytes, d2h_bytes, config_extra, e2e_api, verify_fn = setup_batch8(args, dev, rank, world)
+    else:
+        step_device, step_e2e, h2d_bytes, d2h_bytes, config_extra, e2e_api, verify_fn = setup_screen(args, dev, rank, world)
 
     for _ in range(args.warmup):
         step_device()
@@ -266,119 +450,296 @@ def main():
     ms = timed(step_device, args.steps)
     launches = _lib.launch_count() - n0
     ms_step = ms / args.steps
-    value = 2 * L / (ms_step * 1e-3) / 1e6
+    value = bp_step / (ms_step * 1e-3) / 1e6
 
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_value = 2 * L / (ms_e2e * 1e-3) / 1e6
-    h2d_fp32 = int(runner.h2d_bytes)
+    e2e = {"value": bp_step / (ms_e2e * 1e-3) / 1e6, "unit": "Mbp/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": d2h_bytes, "api": e2e_api}
 
-    # the same end-to-end step fed with packed bases (1 B/bp, orca_b200.feeder) instead of the reference's fp32 one-hot
-    codes_host = torch.from_numpy(synthetic.random_codes(1, L, 0)).pin_memory()
-
-    def step_e2e_packed():
-        runner.upload(codes_host)
-        maps = runner.forward(mpos, wpos)
-        return maps.cpu() if maps is not None else None
-
-    step_e2e_packed()
-    ms_e2e_packed = timed(step_e2e_packed, args.steps) / args.steps
-    h2d_packed = int(runner.h2d_bytes)
-    runner.upload(seq_host)  # back to the fp32 window for the roofline leg
+    if args.workload in ("32mb", "256mb"):
+        if world == 1:
+            # the same call on a PAGEABLE numpy array (what orca_predict's callers hold): pinned staging + pipelined upload inside
+            step_api(seq_np)
+            ms_pg = timed(lambda: step_api(seq_np), args.steps) / args.steps
+            e2e["pageable_numpy"] = {"value": bp_step / (ms_pg * 1e-3) / 1e6, "ms_per_step": ms_pg,
+                                     "note": "same API call fed with a pageable numpy float32 (1, L, 4) array"}
+            # and through the sharded runner (staged upload overlapped with the first encoder chunk)
+            step_e2e_sharded(seq_host)
+            ms_sh = timed(lambda: step_e2e_sharded(seq_host), args.steps) / args.steps
+            e2e["sharded_runner"] = {"value": bp_step / (ms_sh * 1e-3) / 1e6, "ms_per_step": ms_sh, "h2d_bytes_per_step": int(runner.h2d_bytes)}
+        # the same end-to-end step fed with packed bases (1 B/bp, orca_b200.feeder) instead of the reference's fp32 one-hot
+        codes_host = torch.from_numpy(synthetic.random_codes(1, L, 0)).pin_memory()
+        step_e2e_sharded(codes_host)
+        ms_e2e_packed = timed(lambda: step_e2e_sharded(codes_host), args.steps) / args.steps
+        e2e["packed_bases"] = {"value": bp_step / (ms_e2e_packed * 1e-3) / 1e6, "ms_per_step": ms_e2e_packed,
+                               "h2d_bytes_per_step": int(runner.h2d_bytes),
+                               "note": "same step with the sequence uploaded as 1 B/bp packed bases (orca_b200.feeder)"}
+        runner.upload(seq_host)  # back to the fp32 window for the roofline leg
 
     # roofline leg: same steps with per-launch CUDA events around every conv kernel
     _lib.profile_enable(True)
     ms_prof = timed(step_device, args.steps) / args.steps
     prof = _lib.profile_summary()
     _lib.profile_enable(False)
-    clocks = sampler.summary()  # sampled across the three timed legs (value, e2e, per-kernel events)
+
+    # the fp32-grade figure (every encoder stage in the three-product format) beside the default-precision `value`
+    value_fp32_grade = None
+    if args.enc_fp16_stages < 0 and args.kernels != "simt":
+        _lib.set_encoder_fp16_stages(0)
+        step_device()
+        ms32 = timed(step_device, args.steps) / args.steps
+        value_fp32_grade = {"value": bp_step / (ms32 * 1e-3) / 1e6, "ms_per_step": ms32,
+                            "note": "same step with encoder_fp16_stages = 0: fp32-grade bf16 hi/lo three-product arithmetic everywhere"}
+        _lib.set_encoder_fp16_stages(-1)
+        step_device()
+    clocks = sampler.summary()  # sampled across the timed legs
+    if args.workload in ("32mb", "256mb"):
+        config_extra["fp16_range_guard_fired"] = bool(runner.fp16_guard())  # checked once, after the timed legs
+
+    if args.verify:
+        if args.workload == "32mb":
+            parity = verify_32mb(dev, rank, world)
+        elif verify_fn is not None:
+            parity = verify_fn()
+        if world > 1 and args.workload == "32mb":
+            t = torch.tensor([parity if rank == 0 else 0.0], device=dev)
+            dist.broadcast(t, 0)
+            parity = float(t.item())
+
     if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-        with open(os.path.join(ROOT, "gpurun_out", "conv_profile_n%d.json" % world), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", "conv_profile_%s_n%d.json" % (args.workload, world)), "w") as f:
             json.dump({"steps": args.steps, "ms_per_step_profiled": ms_prof, "kernels": prof}, f, indent=1)
-    # group the per-shape records by kernel: (c_in, c_out, Conv1d|Conv2d, tcgen05|simt); Conv1d records carry dil = 0
-    groups = {}
-    for r in prof:
-        key = (r["c_in"], r["c_out"], "conv1d_k9" if r["dil"] == 0 else ("decoder_program" if r["c_in"] < 0 else "conv2d_3x3"),
-               {0: "simt fp32", 1: "tcgen05 bf16x3", 2: "tcgen05 fp16x1"}[r["tc"]])
-        grp = groups.setdefault(key, {"ms": 0.0, "launches": 0, "flop": 0.0})
-        grp["ms"] += r["ms"]; grp["launches"] += r["launches"]; grp["flop"] += r["flop"]
-    roofline = None
-    if groups:
-        key, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        dur_ms = dom["ms"] / dom["launches"]
-        achieved = dom["flop"] / dom["launches"] / (dur_ms * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
-        split = 3 if key[3] == "tcgen05 bf16x3" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
-        # DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_prof_*.md, dram__bytes_read.sum +
-        # dram__bytes_write.sum), scaled to this run's work per launch:
-        #   decoder_program (118-conv Decoder at batch 2, S = 250): 0.69 GB read + 2.29 GB written per launch -- every layer's
-        #     output map is written back (the rotating activation buffers of two images exceed what L2 keeps dirty)
-        #   conv1d 64->64 fp16x1: 0.512 GB read + 0.471 GB written per 4.224 M positions (= algorithmic 2 x 64 ch x 2 B)
-        #   conv1d 64->64 bf16x3: 1.024 GB + 0.978 GB per 4.224 M positions (r01 capture of the three-product kernel)
-        traffic = None
-        per_launch_flop = dom["flop"] / dom["launches"]
-        if key[2] == "decoder_program":
-            traffic = 2.98e9 * per_launch_flop / (2 * 290.5e9)   # ncu launch: 2 maps x 290.5 GFLOP
-        elif key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 fp16x1":
-            traffic = 232.8 * per_launch_flop / (2 * 9 * 64 * 64)
-        elif key[:3] == (64, 64, "conv1d_k9") and key[3] == "tcgen05 bf16x3":
-            traffic = 474.0 * per_launch_flop / (2 * 9 * 64 * 64)
-        label = lambda k: ("%s, %d convs (%s)" % (k[2], k[1], k[3])) if k[2] == "decoder_program" else "%s %d->%d (%s)" % (k[2], k[0], k[1], k[3])
-        breakdown = []
-        for k, gk in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
-            ach = gk["flop"] / (gk["ms"] * 1e-3) / 1e12
-            sp = 3 if k[3] == "tcgen05 bf16x3" else 1
-            breakdown.append({"kernel": label(k), "ms_per_step": gk["ms"] / args.steps, "launches_per_step": gk["launches"] // args.steps,
-                              "achieved_tflops": ach, "frac": ach / peak, "issued_mma_frac": ach * sp / peak})
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
-                    "kernel": label(key),
-                    "issued_mma_tflops": achieved * split, "issued_mma_frac": achieved * split / peak,
-                    "note": "achieved = ALGORITHMIC conv FLOP (2*positions*c_in*c_out*9) per launch / launch time of the kernel with "
-                            "the largest share of the step; it issues %dx that many tensor-core FLOP (%s). `kernels` lists every "
-                            "conv kernel family the same way." % (split, "fp32-parity bf16 hi/lo split" if split == 3 else "single fp16 product"),
-                    "avg_launch_ms": dur_ms, "launches_per_step": dom["launches"] // args.steps,
-                    "share_of_step": dom["ms"] / args.steps / ms_prof, "ms_per_step_profiled": ms_prof,
-                    "conv_ms_per_step": sum(r["ms"] for r in prof) / args.steps, "kernels": breakdown}
+    roofline = build_roofline(prof, peaks, args.steps, ms_prof)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC if args.workload != "screen" else "Mbp/s screened (1 Mb windows/s = contact maps/s beside it)",
+                "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "scaling": "strong", "vs_baseline": None,
                 "dtype": ("f32" if args.kernels == "simt" else
                           "bf16x3 (fp32 operands split hi+lo, 3 tcgen05 products, fp32 accumulate)" if enc16 == 0 else
                           "fp16 (1 tcgen05 product, fp32 accumulate) in encoder stages 1-%d; bf16x3 (operands split hi+lo, 3 products) "
                           "in the other stages, the U-nets and the decoders" % enc16),
                 "data": "synthetic",
-                "config": {"workload": workload,
-                           "seq_len": L, "strands": 2, "models": 1, "kernels": args.kernels, "encoder_fp16_stages": enc16,
-                           "l2": "inputs (512 MB) and stage activations (>1 GB per chunk) exceed the 126 MB L2",
-                           "parallelism": "sequence-sharded encoder x%d + all-gather, strand-parallel cascades" % world
-                           if world > 1 else "single GPU"},
-                "contact_maps_per_s": maps_per_step / (ms_step * 1e-3),
-                "algorithmic_tflops": 2 * flop_per_strand / (ms_step * 1e-3) / 1e12,
-                "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": h2d_fp32, "d2h_bytes_per_step": int(runner.d2h_bytes),
-                        "packed_bases": {"value": 2 * L / (ms_e2e_packed * 1e-3) / 1e6, "ms_per_step": ms_e2e_packed,
-                                         "h2d_bytes_per_step": h2d_packed,
-                                         "note": "same step with the sequence uploaded as 1 B/bp packed bases (orca_b200.feeder)"}},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+                "config": dict({"workload": label, "kernels": args.kernels, "encoder_fp16_stages": enc16}, **config_extra),
+                "contact_maps_per_s": maps_step / (ms_step * 1e-3),
+                "algorithmic_tflops": flop_step / (ms_step * 1e-3) / 1e12,
+                "value_fp32_grade": value_fp32_grade,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if parity is not None:
+            line["parity_relerr"] = parity
+        if world == 1:
+            line["peaks_in_run"] = measure_matmul_peaks(dev)
+        if world == 1 and args.workload == "32mb" and not args.no_gpu_reference:
+            g = gpu_reference(dev, seq_host, mpos, wpos, max(args.steps, 2), 3)
+            ours = runner.forward(mpos, wpos).cpu().numpy()
+            scale = float(np.abs(g["fp32_maps"]).max())
+            line["gpu_reference"] = {
+                "what": "the reference graph (torch.nn.functional restatement, same operators) under eager PyTorch + cuDNN on this B200, "
+                        "one full 32 Mb pass (both strands, blockwise encoder, 12 decoder calls + 2 Decoder_1m)",
+                "tf32_ms": g["tf32_ms"], "fp32_ms": g["fp32_ms"],
+                "tf32_mbp_s": bp_step / (g["tf32_ms"] * 1e-3) / 1e6, "fp32_mbp_s": bp_step / (g["fp32_ms"] * 1e-3) / 1e6,
+                "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+                "relerr_tf32_vs_fp32": float(np.abs(g["tf32_maps"] - g["fp32_maps"]).max() / scale),
+                "relerr_ours_vs_fp32": float(np.abs(ours - g["fp32_maps"]).max() / scale)}
+            line["vs_gpu_reference"] = {"vs_tf32": value / line["gpu_reference"]["tf32_mbp_s"],
+                                        "vs_fp32": value / line["gpu_reference"]["fp32_mbp_s"],
+                                        "fp32_grade_vs_fp32": (value_fp32_grade["value"] / line["gpu_reference"]["fp32_mbp_s"]) if value_fp32_grade else None}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             one = cpu_sample(threads)
             one()
             t0 = time.perf_counter()
             tb, te, td, tm = one()
-            # 256 Mb: 320 blocks, pooling half of Encoder2 at 64000 bins (8 x 1/3 of the timed 8000-bin U-net), 4 decoders
-            full = 2 * (320 * tb + 8 * te / 3 + 4 * td) if big else cpu_extrapolate(tb, te, td, tm)
+            full = cpu_full_seconds(args.workload, tb, te, td, tm, args.screen_windows)
             line["cpu_baseline"] = {
-                "value": 2 * L / full / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
-                "sample": CPU_SAMPLE + "; extrapolated linearly to the full 2-strand step",
-                "sample_wall_s": time.perf_counter() - t0,
-                "maps_per_s": maps_per_step / full}
+                "value": bp_step / full / 1e6, "unit": "Mbp/s", "cores": threads, "kind": "port",
+                "sample": CPU_SAMPLE + "; extrapolated linearly to the full step", "extrapolated": True,
+                "sample_wall_s": time.perf_counter() - t0, "cpu": cpu_model(), "torch_threads": threads,
+                "maps_per_s": maps_step / full}
         print(json.dumps(line))
+    if args.verify and parity is not None and parity > 1e-3:
+        raise SystemExit("parity check failed: relerr %.3e > 1e-3" % parity)
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_roofline(prof, peaks, steps, ms_prof):
+    # group the per-shape records by kernel: (c_in, c_out, Conv1d|Conv2d, tcgen05|simt); Conv1d records carry dil = 0
+    groups = {}
+    for r in prof:
+        key = (r["c_in"], r["c_out"], "conv1d_k9" if r["dil"] == 0 else ("decoder_stream" if r["c_in"] < 0 else "conv2d_3x3"),
+               {0: "simt fp32", 1: "tcgen05 bf16x3", 2: "tcgen05 fp16x1"}[r["tc"]])
+        grp = groups.setdefault(key, {"ms": 0.0, "launches": 0, "flop": 0.0})
+        grp["ms"] += r["ms"]; grp["launches"] += r["launches"]; grp["flop"] += r["flop"]
+    if not groups:
+        return None
+    key, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    dur_ms = dom["ms"] / dom["launches"]
+    achieved = dom["flop"] / dom["launches"] / (dur_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    split = 3 if key[3] == "tcgen05 bf16x3" else 1  # bf16 hi/lo split: 3 tensor-core products per algorithmic product
+    label = lambda k: ("%s, %d convs (%s)" % (k[2], k[1], k[3])) if k[2] == "decoder_stream" else "%s %d->%d (%s)" % (k[2], k[0], k[1], k[3])
+    # DRAM bytes per launch: never a literal -- looked up in the committed ncu capture table and scaled by the work per launch
+    traffic, traffic_src = None, None
+    tab = committed_traffic()
+    tkey = "decoder_stream" if key[2] == "decoder_stream" else "%s_%d_%d_%s" % (key[2], key[0], key[1], "fp16" if split == 1 else "bf16x3")
+    if tkey in tab and tab[tkey].get("flop"):
+        traffic = tab[tkey]["dram_bytes"] * (dom["flop"] / dom["launches"]) / tab[tkey]["flop"]
+        traffic_src = tab[tkey].get("source")
+    breakdown = []
+    for k, gk in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+        ach = gk["flop"] / (gk["ms"] * 1e-3) / 1e12
+        sp = 3 if k[3] == "tcgen05 bf16x3" else 1
+        breakdown.append({"kernel": label(k), "ms_per_step": gk["ms"] / steps, "launches_per_step": gk["launches"] // steps,
+                          "achieved_tflops": ach, "frac": ach / peak, "issued_mma_frac": ach * sp / peak})
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
+            "kernel": label(key),
+            "issued_mma_tflops": achieved * split, "issued_mma_frac": achieved * split / peak,
+            "note": "achieved = ALGORITHMIC conv FLOP (2*positions*c_in*c_out*9) per launch / launch time of the kernel with "
+                    "the largest share of the step; it issues %dx that many tensor-core FLOP (%s). `kernels` lists every "
+                    "conv kernel family the same way." % (split, "fp32-parity bf16 hi/lo split" if split == 3 else "single fp16 product"),
+            "avg_launch_ms": dur_ms, "launches_per_step": dom["launches"] // steps,
+            "share_of_step": dom["ms"] / steps / ms_prof, "ms_per_step_profiled": ms_prof,
+            "conv_ms_per_step": sum(r["ms"] for r in prof) / steps, "kernels": breakdown}
+
+
+def verify_32mb(dev, rank, world):
+    """The fixture configuration of tests/golden/genomepredict_32mb.npz (maps produced by the UNMODIFIED
+    orca_predict.genomepredict on reference modules: shell seed 7, sequence seed 105, mpos 16.5 Mb) through the SAME
+    sharded runner the timed steps use, at this world size.  Returns max over the 6 maps of max|ours - ref| / max|ref|."""
+    import torch
+    from orca_b200 import models, parallel, synthetic
+    g = np.load(os.path.join(ROOT, "tests", "golden", "genomepredict_32mb.npz"))
+    shell = models.H1esc(seed=int(g["shell_seed"]), device=dev)
+    seq = torch.from_numpy(synthetic.random_sequence(1, SEQ_LEN, int(g["seq_seed"])))
+    runner = parallel.ShardedForward(shell, SEQ_LEN, rank, world, dev)
+    runner.upload(seq)
+    maps = runner.forward(int(g["mpos"]), int(g["wpos"]))
+    if rank != 0:
+        return None
+    maps = maps.cpu().numpy()
+    return max(float(np.abs(maps[i] - g["predictions"][i]).max() / np.abs(g["predictions"][i]).max()) for i in range(6))
+
+
+def _gather_to_rank0(t, rank, world):
+    """Concatenate per-rank result tensors (same shape) on rank 0 over NCCL."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return t
+    bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, bufs, dst=0)
+    return torch.cat(bufs, 0) if rank == 0 else None
+
+
+def setup_batch8(args, dev, rank, world):
+    """BASELINE configs[2]: Hff-like shell, 8 distinct 32 Mb sequences (one synthetic sequence rolled by 8 different
+    offsets), both strands, modules called directly; data parallel over the sequences when world > 1."""
+    import torch
+    from orca_b200 import feeder, models, predict, synthetic
+    if 8 % world:
+        raise SystemExit("batch8 needs a world size that divides 8")
+    L, n_local = SEQ_LEN, 8 // world
+    shell = models.Hff(seed=1, device=dev)
+    base = synthetic.random_codes(1, L, 4)[0]
+    mine = [rank * n_local + i for i in range(n_local)]
+    codes = np.stack([np.roll(base, 1_000_003 * k) for k in mine])                       # (n_local, L) packed bases
+    onehot_host = torch.from_numpy(feeder.to_onehot(codes)).pin_memory()                 # (n_local, L, 4) fp32, as the reference takes it
+    state = {"dev": onehot_host.to(dev)}
+    mpos = wpos = L // 2
+
+    def run(seq_dev):
+        with torch.no_grad():
+            outs = []
+            for b in range(seq_dev.shape[0]):  # one sequence at a time: its two strands are the two lanes of one decoder chain
+                avg, _ = predict._strand_lanes_32mb(shell, seq_dev[b:b + 1], mpos, wpos)
+                outs.append(torch.stack(avg))
+            return torch.stack(outs)  # (n_local, 6, 250, 250)
+
+    def step_device():
+        return _gather_to_rank0(run(state["dev"]), rank, world)
+
+    def step_e2e():
+        seq_dev = onehot_host.to(dev, non_blocking=True)
+        maps = _gather_to_rank0(run(seq_dev), rank, world)
+        return maps.cpu() if maps is not None else None
+
+    def verify():
+        # sample independence + the reference-pinned 32 Mb fixture through the same code path
+        with torch.no_grad():
+            a = run(state["dev"][:1])
+            b = run(state["dev"])[:1]
+        assert torch.equal(a, b), "a batch element must not depend on its neighbours"
+        return verify_32mb(dev, 0, 1)
+    cfg = {"seq_len": L, "strands": 2, "models": 1, "batch": 8, "l2": "inputs (512 MB per sequence) exceed the 126 MB L2",
+           "parallelism": "data parallel over the 8 sequences x%d, maps gathered on rank 0" % world if world > 1 else "single GPU"}
+    return step_device, step_e2e, int(onehot_host.numel() * 4), int(8 * 6 * 250 * 250 * 4 if rank == 0 else 0), cfg, \
+        "orca_b200 modules called directly (Encoder -> Encoder2 -> cascade), pinned fp32 one-hot host input", verify
+
+
+def setup_screen(args, dev, rank, world):
+    """BASELINE configs[4]: W 1 Mb windows sliding along a synthetic chromosome (stride 15,625 bp), each through Encoder +
+    level-1 Decoder (no coarse input) + Decoder_1m; data parallel over the windows when world > 1."""
+    import torch
+    import torch.distributed as dist
+    from orca_b200 import models, predict, synthetic
+    W, MB, stride = args.screen_windows, args.micro_batch, 15625
+    if W % (world * MB):
+        raise SystemExit("screen: the window count must be a multiple of world size x micro batch")
+    n_local = W // world
+    shell = models.H1esc(seed=0, device=dev)
+    G = 1_000_000 + (W - 1) * stride
+    genome_host = torch.from_numpy(synthetic.random_codes(1, G, 7)[0]).pin_memory()  # packed bases, 1 B/bp (65 MB at W = 4096)
+    state = {"dev": genome_host.to(dev)}
+    d1 = predict._log_normmat(shell, 1, dev)
+    first = rank * n_local
+
+    def run(genome_dev):
+        with torch.no_grad():
+            out = torch.empty((n_local, 250, 250), dtype=torch.float32, device=dev)
+            for i in range(0, n_local, MB):
+                # a micro-batch of overlapping windows is a strided VIEW of the packed chromosome: no copies
+                x = genome_dev.as_strided((MB, 1_000_000), (stride, 1), (first + i) * stride)
+                e = shell.net0(x, guard=False)
+                out[i:i + MB] = (shell.denets[1](e, d1.expand(MB, -1, -1, -1)) + shell.denet_1_pt(e))[:, 0]
+            return out
+
+    def step_device():
+        return _gather_to_rank0(run(state["dev"]), rank, world)
+
+    def step_e2e():
+        genome_dev = genome_host.to(dev, non_blocking=True)
+        maps = _gather_to_rank0(run(genome_dev), rank, world)
+        return maps.cpu() if maps is not None else None
+
+    def verify():
+        # the first window of this rank against the oracle (CPU): Encoder 1 Mb -> Decoder(level 1, no coarse) + Decoder_1m
+        oracle = _oracle()
+        from orca_b200 import feeder, modules
+        with torch.no_grad():
+            ours = run(state["dev"])[0].cpu().numpy()
+            x = torch.from_numpy(feeder.to_onehot(genome_host[first * stride:first * stride + 1_000_000].numpy()[None])).transpose(1, 2)
+            sd = lambda m, s: synthetic.fill_state_dict(m.state_dict(), s)
+            e = oracle.encoder_forward(sd(modules.Encoder(), 0), x)
+            ref = (oracle.decoder_forward(sd(modules.Decoder(upsample_mode="bilinear"), 10), e, d1.cpu(), None, "bilinear")
+                   + oracle.decoder_1m_forward(sd(modules.Decoder_1m(), 3), e))[0, 0].numpy()
+        err = float(np.abs(ours - ref).max() / np.abs(ref).max())
+        if shell.net0.fp16_guard_fired():
+            raise SystemExit("screen: the fp16 range guard fired")
+        if world > 1:
+            t = torch.tensor([err], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            err = float(t.item())
+        return err
+    cfg = {"windows": W, "window_bp": 1_000_000, "stride_bp": stride, "micro_batch": MB, "models": 1,
+           "l2": "the stage-1 activations of one micro batch (8 Mb x 64 ch) exceed the 126 MB L2",
+           "parallelism": "data parallel over the windows x%d, maps gathered on rank 0" % world if world > 1 else "single GPU"}
+    return step_device, step_e2e, int(G), int(W * 250 * 250 * 4 if rank == 0 else 0), cfg, \
+        "orca_b200 modules called directly on strided views of the packed chromosome (1 B/bp), pinned host input", verify
 
 
 if __name__ == "__main__":

@@ -2,9 +2,10 @@
 ORACLE -- test infrastructure only.  A CPU fp32 restatement of the Orca forward path in plain
 ``torch.nn.functional`` calls, operating directly on a reference-format ``state_dict``.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
-legs may import this module, and only as the checker / the CPU baseline; nothing under
-``orca_b200/`` imports it and the product path never falls back to it.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s comparator legs -- cpu_baseline / ``--impl reference``
+(this graph on the host CPU) and ``gpu_reference`` (the same stock-operator graph on CUDA tensors, i.e. the reference's own
+eager PyTorch + cuDNN GPU path, timed beside ours) -- may import this module, and only as the checker / the baseline;
+nothing under ``orca_b200/`` imports it and the product path never falls back to it.
 
 Why a restatement: the reference (pure Python, /root/reference/orca_modules.py) is importable in
 the build container but does not exist on the GPU box.  The arithmetic itself lives in a
