@@ -21,8 +21,8 @@
 //    them and publishes the row flag.  Maps carry no padding pixels (out-of-bounds zero fill), so the four hot buffers
 //    of a batch-2 decoder (2 x 32 MB + 2 x 16 MB) fit the 126 MB L2.
 //
-// Roles per CTA (352 threads, 1 CTA / SM, cooperative launch so that every CTA is resident): warp 0 = TMA producer
-// (flag polling, runs, weights, residual tiles), warp 1 = MMA issuer, warps 2-9 = epilogue, warp 10 = store + publish.
+// Roles per CTA (384 threads, 1 CTA / SM, cooperative launch so that every CTA is resident): warp 0 = TMA producer
+// (flag polling, runs, weights, residual tiles), warp 1 = MMA issuer, warps 2-9 = epilogue, warps 10-11 = store + publish.
 #include <cuda.h>
 
 #include <cstdio>
@@ -40,7 +40,8 @@ namespace {
 using namespace tcdev;
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreadsS = 32 * (3 + kEpiWarps);
+constexpr int kStoreWarps = 2;
+constexpr int kThreadsS = 32 * (2 + kEpiWarps + kStoreWarps);
 constexpr int kMaxNA = 4;
 constexpr int kAcc = 4;              // TMEM accumulator slots of 128 columns
 constexpr int kSmemCarve = 230400;   // 225 KB of operand / staging space (1024-aligned base; barriers + bias above it)
@@ -63,6 +64,7 @@ struct SLayer {
 struct SGeom {
   unsigned int* flags;  // [n_layers][nb][S] completed tiles per image row
   unsigned int* done;   // [n_layers] CTAs that finished the layer
+  const int2* parts;    // [grid][nb] (first tile, tile count) of every CTA in every image's chain-major tile order
   int nb, S, tpr, total_tiles, n_layers;
 };
 
@@ -157,25 +159,38 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t lo) { return ((uint64_t)
 struct Seg { int b, tx, r, k0, k1, len; };
 struct Walk {
   int S, d, q, rem, tpr, cur, end, n_tiles;
-  int cur2, end2;  // second piece of the rotated range
-  // The CTA's contiguous range [t0, t1) is walked from t0 + rot: [t0 + rot, t1) then [t0, t0 + rot).  Consecutive layers
-  // with the same dilation advance `rot` by 2, so the first tiles of a layer depend only on tiles the previous layer
-  // finished EARLY (its 2nd..4th), never on the ones it has just stored -- the store -> flag -> load latency of the
-  // dependent chain is then hidden behind the rest of the range instead of stalling every layer boundary.
-  __device__ __forceinline__ void init(const SGeom& g, int d_, int rot) {
-    S = g.S; d = d_; tpr = g.tpr;
-    q = S / d; rem = S - q * d;
-    const int t0 = (int)(((long long)blockIdx.x * g.total_tiles) / gridDim.x);
-    const int t1 = (int)(((long long)(blockIdx.x + 1) * g.total_tiles) / gridDim.x);
-    n_tiles = t1 - t0;
-    const int sft = n_tiles > 0 ? rot % n_tiles : 0;
+  int cur2, end2;  // second piece of a rotated range (single image only)
+  int part, nb, img_tiles;
+  const int2* parts;
+  // A CTA owns one contiguous piece of EVERY image (SGeom::parts) and walks them image by image.  With two or more
+  // images the tiles of image b in layer l+1 depend on what this and the other CTAs finished half a layer ago (they have
+  // all been working on the other images since), so the store -> flag -> load latency of the dependent chain and the
+  // all-to-all dependency at a change of dilation are hidden behind useful work instead of stalling every layer.
+  // With a single image the piece is walked from `rot` instead ([t0 + rot, t1) then [t0, t0 + rot), rot advancing by 2
+  // per layer of equal dilation): the first tiles of a layer then depend on tiles the previous layer finished early.
+  __device__ __forceinline__ void load_part(int rot) {
+    const int2 pr = parts[part];
+    const int t0 = part * img_tiles + pr.x, t1 = t0 + pr.y;
+    const int sft = (nb == 1 && pr.y > 0) ? rot % pr.y : 0;
     cur = t0 + sft; end = t1;
     cur2 = t0; end2 = t0 + sft;
   }
+  __device__ __forceinline__ void init(const SGeom& g, int d_, int rot) {
+    S = g.S; d = d_; tpr = g.tpr; nb = g.nb; img_tiles = g.tpr * g.S;
+    q = S / d; rem = S - q * d;
+    parts = g.parts + (size_t)blockIdx.x * g.nb;
+    n_tiles = 0;
+    for (int b = 0; b < nb; ++b) n_tiles += parts[b].y;
+    part = 0;
+    load_part(rot);
+    rot_ = rot;
+  }
+  int rot_;
   __device__ __forceinline__ bool next(Seg& s) {
-    if (cur >= end) {
-      if (cur2 >= end2) return false;
-      cur = cur2; end = end2; cur2 = end2;
+    while (cur >= end) {
+      if (cur2 < end2) { cur = cur2; end = end2; cur2 = end2; break; }
+      if (++part >= nb) return false;
+      load_part(rot_);
     }
     const int img = cur / S, p = cur - img * S;
     s.b = img / tpr; s.tx = img - s.b * tpr;
@@ -220,30 +235,38 @@ struct Stg {
   }
 };
 
+// Optional event trace of one CTA (compiled in with -DDS_TRACE, tests/cuda/dec_stream_test.cu "trace"): per role and
+// per run / tile {id, t0, t1, t2} in clock64 ticks -- where the time of a layer goes, measured, not modelled.
+#ifdef DS_TRACE
+__device__ unsigned long long* g_ds_trace;  // [4 roles][kTraceEv][4]
+__device__ int g_ds_trace_block = DS_TRACE;
+constexpr int kTraceEv = 8192;
+#define TR(role, idx, slot, val)                                                                     \
+  do {                                                                                               \
+    if (blockIdx.x == g_ds_trace_block && g_ds_trace && (idx) < kTraceEv)                                    \
+      g_ds_trace[((size_t)(role) * kTraceEv + (idx)) * 4 + (slot)] = (unsigned long long)(val);      \
+  } while (0)
+#define TR_NOW() clock64()
+#else
+#define TR(role, idx, slot, val) do { } while (0)
+#define TR_NOW() 0
+#endif
+
 // A-run slot ring.  The number of slots changes from layer to layer, so the phase of a slot's barriers is tracked by a
 // per-slot use counter (identical in the producer and the MMA issuer), and every layer starts again at slot 0.
 struct ARing {
   uint32_t cnt[kMaxNA];
-  uint32_t pos;
+  uint32_t pos, total;
   __device__ __forceinline__ void begin_layer() { pos = 0; }
   __device__ __forceinline__ void take(int NA, uint32_t& slot, uint32_t& use) {
     slot = pos;
     pos = pos + 1 == (uint32_t)NA ? 0u : pos + 1;
     use = cnt[slot]++;
+    ++total;
   }
 };
 
 // ---- producer ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void wait_flags(const unsigned int* f0, unsigned int need0, const unsigned int* f1, unsigned int need1,
-                                           int lane) {
-  // lanes 0 / 1 poll one flag each (two L2 round trips in flight instead of two in series)
-  const unsigned int* f = lane == 0 ? f0 : (lane == 1 ? f1 : nullptr);
-  const unsigned int need = lane == 0 ? need0 : need1;
-  if (f) spin_until(f, need);
-  __syncwarp();
-  fence_async_all();  // the TMA loads that follow (async proxy) must observe what the acquire made visible
-}
-
 __device__ __forceinline__ void producer_layer(const SLayer& L, int l, const SGeom& g, uint32_t smem0, const Bars& B, ARing& ring,
                                                Stg& stg, int lane) {
   ring.begin_layer();
@@ -267,20 +290,57 @@ __device__ __forceinline__ void producer_layer(const SLayer& L, int l, const SGe
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
-    const int k_first = run_first(s), k_last = run_last(s);
+    const int k_first = run_first(s), k_last = run_last(s), n_runs = k_last - k_first + 1;
     const int x0 = s.tx * 128;
+    const int row_base = s.b * g.S + s.r + k_first * L.d;  // row of run j = row_base + j * d
+    // Row flags are polled for a WINDOW of up to 32 upcoming runs at once (lane t <-> run wb + t: one L2 round trip for the
+    // whole window) and remembered as bit masks; a run whose bit is still clear when its turn comes is waited for, then the
+    // window is polled again.  A poll per run in series (~1 us each) made the producer the slowest role of the CTA.
+    uint32_t in_ok = 0, res_ok = 0;
+    int wb = 0;
+    auto poll_window = [&]() {
+      const int j = wb + lane;
+      bool oi = true, orr = true;
+      if (j < n_runs) {
+        if (in_flags) oi = ld_acquire(in_flags + row_base + j * L.d) >= (unsigned)g.tpr;
+        if (res_flags) orr = ld_acquire(res_flags + row_base + j * L.d) >= (unsigned)g.tpr;
+      }
+      in_ok = __ballot_sync(0xffffffffu, oi);
+      res_ok = __ballot_sync(0xffffffffu, orr);
+      fence_async_all();  // the TMA loads that follow (async proxy) must observe what the acquires made visible
+    };
+    if (in_flags || res_flags) poll_window();
+    else in_ok = res_ok = 0xffffffffu;
 #pragma unroll 1
     for (int kk = k_first; kk <= k_last; ++kk) {
       const int row = s.b * g.S + s.r + kk * L.d;
+      const int j = kk - k_first;
       // residual tile that goes with this run: tile kk-1 (its last run is this one), plus tile kk when the chain ends here
       const int rt0 = (kk - 1 >= s.k0 && kk - 1 < s.k1) ? kk - 1 : -1;
       const int rt1 = (kk == s.len - 1 && kk >= s.k0 && kk < s.k1) ? kk : -1;
-      const unsigned int* f_in = in_flags ? in_flags + row : nullptr;
-      const unsigned int* f_res = (res_flags && rt0 >= 0) ? res_flags + (s.b * g.S + s.r + rt0 * L.d) : nullptr;
-      if (f_in || f_res) wait_flags(f_in, (unsigned)g.tpr, f_res, (unsigned)g.tpr, lane);
+      TR(0, ring.total, 0, ((unsigned long long)l << 32) | (unsigned)kk);
+      TR(0, ring.total, 1, TR_NOW());
+      if (in_flags || res_flags) {
+        if (j - wb >= 32) { wb = j; poll_window(); }
+        const bool need_in = in_flags && !((in_ok >> (j - wb)) & 1u);
+        // (a residual row one run back can only precede the window right after the window moved: re-check it then)
+        const bool need_r0 = res_flags && rt0 >= 0 && (j - 1 < wb || !((res_ok >> (j - 1 - wb)) & 1u));
+        const bool need_r1 = res_flags && rt1 >= 0 && !((res_ok >> (j - wb)) & 1u);
+        if (need_in || need_r0 || need_r1) {
+          const unsigned int* f = nullptr;
+          if (lane == 0 && need_in) f = in_flags + row;
+          if (lane == 1 && need_r0) f = res_flags + row - L.d;
+          if (lane == 2 && need_r1) f = res_flags + row;
+          if (f) spin_until(f, (unsigned)g.tpr);
+          __syncwarp();
+          poll_window();  // refresh: later rows have usually completed meanwhile
+        }
+      }
+      TR(0, ring.total, 2, TR_NOW());
       uint32_t slot, ause;
       ring.take(L.NA, slot, ause);
       mbar_wait(B.a_empty + 8 * slot, (ause & 1u) ^ 1u);
+      TR(0, ring.total - 1, 3, TR_NOW());
       if (elect_one()) {
         mbar_expect_tx(B.a_full + 8 * slot, slot_tx);
         const uint32_t dst = smem0 + L.offA + slot * L.a_slot_bytes;
@@ -293,7 +353,6 @@ __device__ __forceinline__ void producer_layer(const SLayer& L, int l, const SGe
         for (int e = 0; e < 2; ++e) {
           const int kt = e == 0 ? rt0 : rt1;
           if (kt < 0) continue;
-          if (e == 1 && res_flags) wait_flags(res_flags + (s.b * g.S + s.r + kt * L.d), (unsigned)g.tpr, nullptr, 0, lane);
           uint32_t ss, use, ruse;
           stg.take(L.NS, tile_it, true, ss, use, ruse);
           ++tile_it;
@@ -351,6 +410,8 @@ __device__ __forceinline__ void mma_layer(const SLayer& L, int l, const SGeom& g
     for (int kk = k_first; kk <= k_last; ++kk) {
       uint32_t slot, ause;
       ring.take(L.NA, slot, ause);
+      TR(1, ring.total - 1, 0, ((unsigned long long)l << 32) | (unsigned)kk);
+      TR(1, ring.total - 1, 1, TR_NOW());
       // tiles this run contributes to: kt = kk+1 (dy = -d, image row above the output), kk, kk-1
       bool val[3], fresh[3], last[3];
       uint32_t acc[3];
@@ -366,8 +427,10 @@ __device__ __forceinline__ void mma_layer(const SLayer& L, int l, const SGeom& g
           mbar_wait(B.acc_empty + 8 * (acc[dyi] % kAcc), ((acc[dyi] / kAcc) & 1u) ^ 1u);
         }
       }
+      TR(1, ring.total - 1, 2, TR_NOW());
       mbar_wait(B.a_full + 8 * slot, ause & 1u);
       tc_fence_after();
+      TR(1, ring.total - 1, 3, TR_NOW());
       const uint32_t aBase = smem0 + L.offA + slot * L.a_slot_bytes;
       const uint32_t aHi = __shfl_sync(0xffffffffu, aBase >> 4, 0);
       const uint32_t aLo = __shfl_sync(0xffffffffu, (aBase + (C_IN == 64 ? (uint32_t)L.a_box_bytes : 64u)) >> 4, 0);
@@ -410,8 +473,10 @@ __device__ __forceinline__ void epilogue_layer(const SLayer& L, const SGeom& g, 
       uint32_t ss, use, ruse;
       stg.take(L.NS, tile_it, L.tm_res != nullptr, ss, use, ruse);
       ++tile_it;
+      if (warp == 2) { TR(2, acc_it, 0, ((unsigned long long)L.c_out << 32) | (unsigned)kt); TR(2, acc_it, 1, TR_NOW()); }
       mbar_wait(B.acc_full + 8 * as, aph);
       tc_fence_after();
+      if (warp == 2) TR(2, acc_it, 2, TR_NOW());
       float v[NCH];
       {
         uint32_t raw[NCH], raw2[NCH];
@@ -454,6 +519,7 @@ __device__ __forceinline__ void epilogue_layer(const SLayer& L, const SGeom& g, 
                      reinterpret_cast<__nv_bfloat16*>(lo_row + (((lo_c0 + c) ^ sw) << 4)));
       fence_async_smem();  // generic-proxy writes -> visible to the TMA store
       __syncwarp();
+      if (warp == 2) TR(2, acc_it, 3, TR_NOW());
       if (lane == 0) mbar_arrive(B.stg_full + 8 * ss);
       ++acc_it;
     }
@@ -461,7 +527,11 @@ __device__ __forceinline__ void epilogue_layer(const SLayer& L, const SGeom& g, 
 }
 
 // ---- store + publish ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_layer(const SLayer& L, int l, const SGeom& g, uint32_t smem0, const Bars& B, Stg& stg, int lane) {
+// Two store warps: warp `sw` owns staging slot `sw` (layers with one staging tile: warp 0 alone), so the ~1.5 us a store
+// takes to be read out of shared memory, performed and published overlaps with the other warp's tile instead of
+// serialising (measured: one warp made 32->64 layers store-bound at ~2.3 us per tile).
+__device__ __forceinline__ void store_layer(const SLayer& L, int l, const SGeom& g, uint32_t smem0, const Bars& B, Stg& stg, int lane,
+                                            int sw) {
   if (L.war_layer >= 0 && lane == 0) {
     // write-after-read: every CTA must have finished the last layer that READ the buffer this layer overwrites
     spin_until(g.done + L.war_layer, gridDim.x);
@@ -478,25 +548,32 @@ __device__ __forceinline__ void store_layer(const SLayer& L, int l, const SGeom&
       uint32_t ss, use, ruse;
       stg.take(L.NS, tile_it, false, ss, use, ruse);
       ++tile_it;
+      if ((int)ss != sw) continue;              // the other store warp's tile
       mbar_wait(B.stg_full + 8 * ss, use & 1u);
       if (lane == 0) {
+        TR(3, stg.cnt[0] + stg.cnt[1] - 1, 0, ((unsigned long long)l << 32) | (unsigned)kt);
+        TR(3, stg.cnt[0] + stg.cnt[1] - 1, 1, TR_NOW());
         const uint32_t src = smem0 + (ss ? L.offStg1 : L.offStg0);
         const int trow = s.b * g.S + s.r + kt * L.d, x0 = s.tx * 128;
         tma_store_3d(L.tm_out, 0, x0, trow, src);
         if (L.c_out == 64) tma_store_3d(L.tm_out, 64, x0, trow, src + 16384);
         bulk_commit();
         bulk_wait_read0();                      // staging tile read: it may be refilled
+        TR(3, stg.cnt[0] + stg.cnt[1] - 1, 2, TR_NOW());
         B.cnt[ss] = use + 1;                    // (single writer) for the producer's residual loads
         mbar_arrive(B.stg_free + 8 * ss);       // for the epilogue of layers without a residual
         bulk_wait0();                           // writes performed
         fence_async_all();
         __threadfence();
         red_release(flags + trow);              // publish: one more tile of this image row is complete
+        TR(3, stg.cnt[0] + stg.cnt[1] - 1, 3, TR_NOW());
       }
       __syncwarp();
     }
   }
-  if (lane == 0) {
+  __syncwarp();
+  asm volatile("bar.sync 2, %0;" ::"n"(32 * kStoreWarps) : "memory");  // both store warps have published their tiles of this layer
+  if (sw == 0 && lane == 0) {
     B.cnt[2] = (uint32_t)l + 1;
     red_release(g.done + l);
   }
@@ -538,7 +615,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) conv2d_stream_kernel(const SLaye
   uint32_t acc_it = 0;  // accumulator ring position runs across layers
   ARing ring;
   for (int i = 0; i < kMaxNA; ++i) ring.cnt[i] = 0;
-  ring.pos = 0;
+  ring.pos = 0; ring.total = 0;
   Stg stg;
   stg.cnt[0] = stg.cnt[1] = stg.rcnt[0] = stg.rcnt[1] = 0;
   if (warp == 0) {
@@ -568,7 +645,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) conv2d_stream_kernel(const SLaye
     }
   } else {
 #pragma unroll 1
-    for (int l = 0; l < g.n_layers; ++l) { s_role_layer[warp] = l; store_layer(layers[l], l, g, smem0, B, stg, lane); }
+    for (int l = 0; l < g.n_layers; ++l) { s_role_layer[warp] = l; store_layer(layers[l], l, g, smem0, B, stg, lane, warp - (2 + kEpiWarps)); }
   }
   tc_fence_before();
   __syncthreads();
@@ -637,6 +714,14 @@ int ds_debug_read(unsigned int out[184]) {
   ORCA_CUDA_OK(cudaMemcpyFromSymbol(out, g_ds_debug, 184 * sizeof(unsigned int)));
   return ORCA_B200_OK;
 }
+
+#ifdef DS_TRACE
+int ds_trace_set(unsigned long long* dev_buf, int block) {
+  ORCA_CUDA_OK(cudaMemcpyToSymbol(g_ds_trace, &dev_buf, sizeof dev_buf));
+  if (block >= 0) ORCA_CUDA_OK(cudaMemcpyToSymbol(g_ds_trace_block, &block, sizeof block));
+  return ORCA_B200_OK;
+}
+#endif
 
 bool ds_layer_eligible(const ConvLayer& L) {
   return L.kh == 3 && L.kw == 3 && L.dil >= 1 && L.dil <= 64 &&
@@ -790,9 +875,10 @@ int DecStream::add(const ConvLayer& L, int k_half, int use_bias, const DMap& in,
 }
 
 size_t DecStream::scratch_bytes(int max_layers, int nb, int S) {
-  // [flags + done | tensor maps (3 per layer at most, 128 B each) | layer table]
+  // [flags + done | tensor maps (3 per layer at most, 128 B each) | layer table | per-CTA tile ranges]
   const size_t counters = ((size_t)max_layers * nb * S + max_layers) * 4;
-  return ((counters + 255) & ~size_t(255)) + (size_t)3 * max_layers * sizeof(CUtensorMap) + (size_t)max_layers * sizeof(SLayer) + 1024;
+  return ((counters + 255) & ~size_t(255)) + (size_t)3 * max_layers * sizeof(CUtensorMap) + (size_t)max_layers * sizeof(SLayer) +
+         (size_t)256 * nb * sizeof(int2) + 2048;
 }
 
 int DecStream::run(void* scratch, size_t scratch_bytes_, cudaStream_t s) {
@@ -802,7 +888,8 @@ int DecStream::run(void* scratch, size_t scratch_bytes_, cudaStream_t s) {
   g.n_layers = n;
   const size_t counters = (((size_t)n * g.nb * g.S + n) * 4 + 255) & ~size_t(255);
   const size_t maps_bytes = impl->maps.size() * sizeof(CUtensorMap);
-  const size_t need = counters + maps_bytes + (size_t)n * sizeof(SLayer) + 512;
+  const size_t parts_off = counters + ((maps_bytes + 255) & ~size_t(255)) + (((size_t)n * sizeof(SLayer) + 255) & ~size_t(255));
+  const size_t need = parts_off + (size_t)256 * g.nb * sizeof(int2) + 256;
   if (scratch_bytes_ < need || (reinterpret_cast<uintptr_t>(scratch) & 255)) { set_error("DecStream: scratch too small or misaligned"); return ORCA_B200_EWORKSPACE; }
   char* base = static_cast<char*>(scratch);
   g.flags = reinterpret_cast<unsigned int*>(base);
@@ -828,7 +915,37 @@ int DecStream::run(void* scratch, size_t scratch_bytes_, cudaStream_t s) {
     configured_dev[dev & 63] = true;
   }
   const int sms = sms_dev[dev & 63] > 0 ? sms_dev[dev & 63] : 148;
-  const int grid = g.total_tiles < sms ? g.total_tiles : sms;
+  int grid = g.total_tiles < sms ? g.total_tiles : sms;
+  if (grid > 256) grid = 256;
+  {
+    // Every CTA gets a contiguous piece of every image.  Images 0..nb-2 are split evenly; the last image's pieces make
+    // each CTA's TOTAL equal to the even split of all tiles (so the per-CTA totals differ by at most one tile).
+    const int T_img = g.tpr * g.S;
+    std::vector<int2> parts((size_t)grid * g.nb);
+    bool ok = true;
+    int last_start = 0;
+    for (int c = 0; c < grid && ok; ++c) {
+      int total = (int)(((long long)(c + 1) * g.total_tiles) / grid - ((long long)c * g.total_tiles) / grid);
+      for (int b = 0; b < g.nb - 1; ++b) {
+        const int a0 = (int)(((long long)c * T_img) / grid), a1 = (int)(((long long)(c + 1) * T_img) / grid);
+        parts[(size_t)c * g.nb + b] = make_int2(a0, a1 - a0);
+        total -= a1 - a0;
+      }
+      if (total < 0) { ok = false; break; }
+      parts[(size_t)c * g.nb + g.nb - 1] = make_int2(last_start, total);
+      last_start += total;
+    }
+    if (!ok || last_start != T_img) {  // tiny maps with many images: plain even split of every image
+      for (int c = 0; c < grid; ++c)
+        for (int b = 0; b < g.nb; ++b) {
+          const int a0 = (int)(((long long)c * T_img) / grid), a1 = (int)(((long long)(c + 1) * T_img) / grid);
+          parts[(size_t)c * g.nb + b] = make_int2(a0, a1 - a0);
+        }
+    }
+    int2* d_parts = reinterpret_cast<int2*>(base + parts_off);
+    ORCA_CUDA_OK(cudaMemcpyAsync(d_parts, parts.data(), parts.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    g.parts = d_parts;
+  }
   const SLayer* lp = d_layers;
   void* args[] = {(void*)&lp, (void*)&g};
   // cooperative launch: the row flags are spin-waited, so every CTA must be resident (1 per SM)

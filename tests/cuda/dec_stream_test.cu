@@ -370,8 +370,47 @@ static void timing(int nb, int fixed_d = 0) {
   for (auto& m : bufs) CK(cudaFree(m.p));
 }
 
+#ifdef DS_TRACE
+namespace orca { int ds_trace_set(unsigned long long* dev_buf, int block); }
+static void trace(int nb, int block) {
+  const size_t n = (size_t)4 * 8192 * 4;
+  unsigned long long* d;
+  CK(cudaMalloc(&d, n * 8));
+  CK(cudaMemset(d, 0, n * 8));
+  std::mt19937 rng(7);
+  std::vector<int> dils;
+  const int base[7] = {1, 2, 4, 8, 16, 32, 64};
+  for (int r = 0; r < 4; ++r) for (int i = 0; i < 7; ++i) dils.push_back(base[i]);
+  dils.erase(dils.begin());
+  Program P = build_program(dils, true, rng);
+  const int S = 250;
+  auto x = random_map(nb, 64, S, rng);
+  DMap bufs[6];
+  for (int i = 0; i < 3; ++i) bufs[i] = alloc_map(nb, 64, S);
+  for (int i = 3; i < 5; ++i) bufs[i] = alloc_map(nb, 32, S);
+  bufs[5] = upload_map(x, nb, 64, S);
+  run_program(P, bufs, true, 2);      // warm
+  OK(ds_trace_set(d, block));
+  CK(cudaMemset(d, 0, n * 8));
+  run_program(P, bufs, true, 1);      // (its warm-up launch is traced too and then overwritten by the timed one)
+  OK(ds_trace_set(nullptr, -1));
+  std::vector<unsigned long long> h(n);
+  CK(cudaMemcpy(h.data(), d, n * 8, cudaMemcpyDeviceToHost));
+  const char* names[4] = {"producer", "mma", "epilogue", "store"};
+  for (int r = 0; r < 4; ++r)
+    for (int i = 0; i < 8192; ++i) {
+      const unsigned long long* e = &h[((size_t)r * 8192 + i) * 4];
+      if (!e[1] && !e[2] && !e[3]) continue;
+      printf("TRACE %s %d %llu %llu %llu %llu %llu\n", names[r], i, e[0] >> 32, e[0] & 0xffffffffu, e[1], e[2], e[3]);
+    }
+}
+#endif
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+#ifdef DS_TRACE
+  if (argc > 1 && !strncmp(argv[1], "trace", 5)) { trace(argv[1][5] == '1' ? 1 : 2, argc > 2 ? atoi(argv[2]) : 20); return 0; }
+#endif
   if (argc > 1 && !strncmp(argv[1], "time", 4)) {  // "time1" / "time2": only the Decoder-shaped timing run (ncu target)
     timing(argv[1][4] == '1' ? 1 : 2);
     return 0;
