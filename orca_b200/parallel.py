@@ -230,19 +230,28 @@ class ShardedForward:
             for (kind, rev), o in zip(jobs, outs):
                 (preds if kind == "c" else extras)[rev] = o
             if world > 1:  # collect on rank 0: the reverse cascade, and the Decoder_1m terms computed elsewhere
+                # ONE batched group of point-to-point operations (ncclGroupStart/End underneath) instead of three
+                # serialised send/recv pairs
+                ops, landing = [], []
+
                 def move(t_dict, rev, src, shape):
                     if src == 0:
                         return
                     if rank == src:
-                        dist.send(t_dict[rev].contiguous(), dst=0)
+                        ops.append(dist.P2POp(dist.isend, t_dict[rev].contiguous(), 0))
                     elif rank == 0:
                         buf = torch.empty(shape, dtype=torch.float32, device=self.device)
-                        dist.recv(buf, src=src)
-                        t_dict[rev] = buf
+                        ops.append(dist.P2POp(dist.irecv, buf, src))
+                        landing.append((t_dict, rev, buf))
                 move(preds, True, rev_rank, (n_maps, self.n_ch, 250, 250))
                 if has_1m:
                     move(extras, False, x_rank[False], (self.n_ch, 250, 250))
                     move(extras, True, x_rank[True], (self.n_ch, 250, 250))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                for t_dict, rev, buf in landing:
+                    t_dict[rev] = buf
             if rank != 0:
                 return None
             if has_1m:

@@ -21,11 +21,23 @@ class FakeNet0(nn.Module):
         self.register_buffer("w", torch.tensor([0.1, 0.2, 0.3, 0.4]))
         self.register_buffer("ch", torch.linspace(0.5, 1.5, 128))
 
-    def forward(self, x, reverse_complement=False):
+    def forward(self, x, reverse_complement=False, bin_range=None, out=None, window=None):
+        """Reference call: forward(x).  The keyword extensions are those of orca_b200.modules.Encoder.forward (strand
+        flip in place, a shard's bin range / window / output buffer) so that the sharded runner can drive this fake."""
+        if window is not None:  # a shard holds positions [pos0, pos0 + n) of an L_total sequence
+            pos0, L_total = window
+            full = torch.zeros((x.shape[0], 4, L_total), dtype=x.dtype)
+            full[:, :, pos0:pos0 + x.shape[2]] = x
+            x = full
         if reverse_complement:  # orca_b200's native signature; the reference passes the flipped copy instead
             x = x.flip(1).flip(2)
         B, _, L = x.shape
         P = L // self.bin_bp
+        if bin_range is not None:
+            enc = self.forward(x).transpose(1, 2)  # (B, P, 128)
+            b0, b1 = bin_range
+            out[:, b0:b1] = enc[:, b0:b1]
+            return out.transpose(1, 2)
         t = (x * self.w[None, :, None]).sum(1).reshape(B, P, self.bin_bp).mean(2)
         pos = torch.arange(P, dtype=torch.float32) / P
         e = t * (1.0 + pos)[None, :] + 0.05 * torch.sin(pos * 40.0)[None, :]

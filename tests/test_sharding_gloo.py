@@ -74,3 +74,45 @@ def test_sharded_encode_matches_unsharded():
         ref_r = oracle.encoder_run(sd, torch.from_numpy(np.ascontiguousarray(seq[:, ::-1, ::-1])).transpose(1, 2))
     assert torch.allclose(ret["fwd"], ref_f, atol=2e-6)
     assert torch.allclose(ret["rev"], ref_r, atol=2e-6)
+
+
+def _cascade_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fakes
+    from orca_b200 import parallel
+    shell = fakes.FakeShell("h1esc")
+    seq = torch.from_numpy(fakes.stub_sequence(32_000_000, 111))
+    fwd = parallel.ShardedForward(shell, 32_000_000, rank, world, torch.device("cpu"))
+    fwd.upload(seq)
+    maps = fwd.forward(16_500_000, 16_000_000)
+    assert (maps is None) == (rank != 0)
+    if rank == 0:
+        ret["maps"] = maps.clone()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_forward_distribution_matches_single_process(world):
+    """The WHOLE sharded forward on `world` ranks (gloo): sharded encode + all-gather, the strand cascades on ranks 0 / 1,
+    the Decoder_1m terms on ranks 2 / 3 when they exist, the batched point-to-point collection on rank 0 and the strand
+    average -- against the single-process driver on the same stand-in networks (tests/fakes.py), whose maps depend on
+    every crop index of both strands."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fakes
+    from orca_b200 import predict
+    port = 31500 + os.getpid() % 2000 + world
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cascade_worker, args=(world, port, ret), nprocs=world, join=True)
+    shell = fakes.FakeShell("h1esc")
+    seq = fakes.stub_sequence(32_000_000, 111)
+    ref = predict._genomepredict_on(torch.device("cpu"), seq, "chrS", 16_500_000, 16_000_000, [shell])
+    want = np.stack(ref["predictions"][0])
+    got = ret["maps"].numpy()
+    assert got.shape == want.shape == (6, 250, 250)
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
