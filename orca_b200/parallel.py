@@ -12,6 +12,8 @@ un-sharded: the forward-strand cascade on rank 0, the reverse-complement cascade
 For the reverse strand a rank encodes the MIRRORED bins [P-b1, P-b0): they read exactly the same
 forward-strand window walked backwards, so one upload serves both strands.
 """
+import threading
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -48,6 +50,7 @@ class ShardedForward:
         self.window = None
         self.background, self.chrlen = None, None
         self._copy_stream = None
+        self._uploader, self._staging, self._staging_ev = None, None, None
         self._ready = None
         self._cuts = [self.b0, self.b1]
         self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
@@ -96,6 +99,17 @@ class ShardedForward:
             self.window = torch.empty((1, n) if packed else (1, n, 4), dtype=sl.dtype, device=self.device)
         cs = self._copy_stream
         cs.wait_stream(main)  # earlier kernels may still be reading the previous contents
+        self._join_uploader()
+        if not sl.is_pinned() and sl.numel() * sl.element_size() >= (64 << 20):
+            # PAGEABLE host memory (what orca_predict's callers hold): a helper thread copies it through two pinned
+            # staging buffers piece by piece; the main thread goes on to enqueue the encoder, which starts on piece 1
+            # while the helper is still staging the rest (torch copies release the GIL).
+            events = [torch.cuda.Event() for _ in ends]
+            recorded = [threading.Event() for _ in ends]
+            self._uploader = threading.Thread(target=self._upload_pageable, args=(sl, ends, events, recorded), daemon=True)
+            self._uploader.start()
+            self._ready = list(zip(events, recorded))
+            return self.window
         events, lo = [], 0
         with torch.cuda.stream(cs):
             for hi in ends:
@@ -103,10 +117,43 @@ class ShardedForward:
                     self.window[:, lo:hi].copy_(sl[:, lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-                events.append(ev)
+                events.append((ev, None))
                 lo = max(lo, hi)
         self._ready = events
         return self.window
+
+    _STAGE_ROWS = 1 << 21  # rows (bp) per pinned staging buffer: 32 MB of fp32 one-hot
+
+    def _upload_pageable(self, sl, ends, events, recorded):
+        cs = self._copy_stream
+        row_shape = tuple(sl.shape[2:])
+        if self._staging is None or self._staging[0].dtype != sl.dtype or tuple(self._staging[0].shape[1:]) != row_shape:
+            self._staging = [torch.empty((self._STAGE_ROWS,) + row_shape, dtype=sl.dtype).pin_memory() for _ in range(2)]
+            self._staging_ev = [torch.cuda.Event() for _ in range(2)]
+        k, lo = 0, 0
+        try:
+            with torch.cuda.device(self.device), torch.cuda.stream(cs):
+                for i, hi in enumerate(ends):
+                    while lo < hi:
+                        n = min(self._STAGE_ROWS, hi - lo)
+                        b = k & 1
+                        if k >= 2:
+                            self._staging_ev[b].synchronize()  # the DMA that last read this staging buffer is done
+                        self._staging[b][:n].copy_(sl[0, lo:lo + n])
+                        self.window[0, lo:lo + n].copy_(self._staging[b][:n], non_blocking=True)
+                        self._staging_ev[b].record(cs)
+                        lo += n
+                        k += 1
+                    events[i].record(cs)
+                    recorded[i].set()
+        finally:
+            for r in recorded:
+                r.set()
+
+    def _join_uploader(self):
+        if self._uploader is not None:
+            self._uploader.join()
+            self._uploader = None
 
     def _encode_local(self, reverse):
         """This rank's bins of one strand -> (1, P, 128) buffer (other bins undefined)."""
@@ -117,15 +164,19 @@ class ShardedForward:
             kw["guard"] = False  # native Encoder: the fp16 range guard is checked once per pass, see fp16_guard()
         x = self.window if self.window.dtype == torch.uint8 else self.window.transpose(1, 2)
         ready, self._ready = (self._ready, None) if not reverse else (None, self._ready)
+        def wait(item):
+            ev, recorded = item
+            if recorded is not None:
+                recorded.wait()  # the helper thread has recorded the event (pageable upload)
+            torch.cuda.current_stream(self.device).wait_event(ev)
         if ready is not None and len(ready) > 1:  # first use after a staged upload (forward strand)
-            main = torch.cuda.current_stream(self.device)
-            for i, ev in enumerate(ready):
-                main.wait_event(ev)
+            for i, item in enumerate(ready):
+                wait(item)
                 self.shell.net0(x, bin_range=(self._cuts[i], self._cuts[i + 1]), **kw)
         else:
             pending = ready or self._ready
             if pending:
-                torch.cuda.current_stream(self.device).wait_event(pending[-1])
+                wait(pending[-1])
                 self._ready = None
             self.shell.net0(x, bin_range=bins, **kw)
         return enc

@@ -228,9 +228,12 @@ def cascade_32mb_lanes(model, lanes, mpos, wpos, inline_1m=True):
     carries one batch element per lane, so the 118 dependent layers of a level are paid once instead of per strand
     (each lane keeps its own crop windows; the arithmetic per lane is exactly cascade_32mb's).
 
-    lanes: [(encodings {level: (B, 128, P/level)}, reverse), ...].  Returns (preds: list over levels of
-    (n_lanes * B, C, 250, 250), lane-major; starts: per-lane start bins)."""
+    lanes: [(encodings {level: (B, 128, P/level)}, reverse[, mpos, wpos]), ...] -- a lane may carry its own zoom target
+    (orca_b200.variants batches the windows of one variant call); otherwise the call's mpos / wpos apply.  Returns
+    (preds: list over levels of (n_lanes * B, C, 250, 250), lane-major; starts: per-lane start bins)."""
     n = len(lanes)
+    target = [(ln[2], ln[3]) if len(ln) > 2 else (mpos, wpos) for ln in lanes]
+    lanes = [(ln[0], ln[1]) for ln in lanes]
     device = lanes[0][0][1].device
     B = lanes[0][0][1].shape[0]
     starts, sidx, preds = [[0] for _ in lanes], [0] * n, []
@@ -242,7 +245,7 @@ def cascade_32mb_lanes(model, lanes, mpos, wpos, inline_1m=True):
         if level == 1 and hasattr(model, "denet_1_pt") and inline_1m:
             pred = pred + model.denet_1_pt.forward(xl)
         for i, (_, rev) in enumerate(lanes):
-            sidx[i] = _next_index_32mb(level, starts[i][j], mpos, wpos, rev)
+            sidx[i] = _next_index_32mb(level, starts[i][j], target[i][0], target[i][1], rev)
             starts[i].append(starts[i][j] + sidx[i] * level)
         preds.append(pred)
     return preds, [st[:-1] for st in starts]
@@ -283,9 +286,59 @@ def _strand_lanes_32mb(model, seq_dev, mpos, wpos):
     return _average_strands([p[:B] for p in preds], [p[B:] for p in preds]), starts[0]
 
 
+def _staged_runners(device, sequence, models):
+    """Single 32 Mb-class sequence held on the HOST + native shells: one cached sharded runner (world size 1) per model, whose
+    staged upload overlaps the PCIe transfer (and, for pageable arrays, the pinned staging) with the first encoder chunks.
+    Returns None when the call does not qualify (device input, batch > 1, foreign modules ...)."""
+    if torch.device(device).type != "cuda" or isinstance(sequence, (str, bytes, bytearray, memoryview)):
+        return None
+    t = torch.from_numpy(sequence) if isinstance(sequence, np.ndarray) else sequence
+    if not isinstance(t, torch.Tensor) or t.is_cuda:
+        return None
+    if t.dtype == torch.uint8:
+        t = t[None] if t.dim() == 1 else t
+        if t.dim() != 2:
+            return None
+    elif t.dtype != torch.float32 or t.dim() != 3 or t.size(2) != 4 or not t.is_contiguous():
+        return None
+    L = t.shape[1]
+    if t.shape[0] != 1 or L % 4000 or L // 4000 < 8000:
+        return None
+    if not all(hasattr(getattr(m, "net0", None), "fp16_guard_fired") for m in models):
+        return None
+    from . import parallel
+    runners = []
+    for m in models:
+        cache = m.__dict__.setdefault("_staged_runner", {})
+        key = (L, str(device))
+        if key not in cache:
+            cache[key] = parallel.ShardedForward(m, L, 0, 1, torch.device(device))
+        runners.append(cache[key])
+    return t, runners
+
+
 def _genomepredict_on(device, sequence, mchr, mpos, wpos, models):
     """Body of genomepredict for shells living on `device` (the host logic is device-agnostic: tests/test_host.py
     drives it on the CPU with stand-in networks against fixtures from the unmodified reference driver)."""
+    staged = _staged_runners(device, sequence, models)
+    if staged is not None:
+        t, runners = staged
+        with torch.no_grad():
+            for attempt in range(2):
+                runners[0].upload(t)
+                for r in runners[1:]:  # every model reads the one uploaded window
+                    r.window, r._ready, r._cuts = runners[0].window, None, runners[0]._cuts
+                outs = []
+                for i, r in enumerate(runners):
+                    if i > 0:
+                        torch.cuda.current_stream(device).wait_stream(runners[0]._copy_stream)
+                    outs.append(r.forward(mpos, wpos))
+                host = [o.cpu().numpy() for o in outs]
+                runners[0]._join_uploader()
+                if not check_fp16_guard(models):
+                    break
+        starts0 = cascade_starts_32mb(mpos, wpos, False)
+        return _output_32mb(host, starts0, mchr, wpos, models)
     with torch.no_grad():
         seq_dev = _to_device_sequence(sequence, device)
         for attempt in range(2):
@@ -295,6 +348,11 @@ def _genomepredict_on(device, sequence, mchr, mpos, wpos, models):
             host = [s.cpu().numpy() for s in stacked]
             if not check_fp16_guard(models):  # else: the encoders now run fp32-grade; repeat the pass once
                 break
+    return _output_32mb(host, starts0, mchr, wpos, models)
+
+
+def _output_32mb(host, starts0, mchr, wpos, models):
+    """The dict orca_predict.genomepredict returns (orca_predict.py:500-540)."""
     output = {"predictions": [[h[j] for j in range(h.shape[0])] for h in host], "experiments": None}
     output["start_coords"] = [wpos - 16000000 + s * 4000 for s in starts0]
     output["end_coords"] = [int(output["start_coords"][ii] + 32000000 / 2 ** ii) for ii in range(6)]

@@ -63,7 +63,7 @@ def test_encoder_golden(name, impl):
     assert e <= tol(impl)
     if impl == "auto":  # encoder precision settings: three-product bf16 everywhere (0), default (3), single-pass fp16 everywhere (7)
         errs = {}
-        for stages in (0, 3, 7):
+        for stages in (0, 3, 4, 5, 7):
             _lib.set_encoder_fp16_stages(stages)
             try:
                 errs[stages] = relerr(m(x).cpu().numpy(), g["out"])
@@ -584,3 +584,34 @@ def test_unmodified_reference_drivers_on_native_shells():
     errs = [relerr(p, r) for p, r in zip(out["predictions"][0], g["predictions"])]
     print("UNMODIFIED orca_predict.genomepredict_256Mb on a native H1esc_256M shell: relerr per level", ["%.1e" % e for e in errs])
     assert max(errs) <= TOL
+
+
+def test_variant_windows_reuse_encoder_blocks():
+    """the windows of one structural-variant call (reference + a deletion allele, as
+    orca_predict.process_del builds them, orca_predict.py:1673-1794) through orca_b200.variants: encoder blocks upstream
+    of the breakpoint are re-used from the cache, all four strand cascades run as one batched chain, and every map is
+    BIT-identical to a separate genomepredict call on that window."""
+    from orca_b200 import feeder, models, predict, variants
+    shell = models.H1esc(seed=7)
+    L = 32_000_000
+    ref = synthetic.random_codes(1, L, 105)[0]
+    bp, dlen = 20_300_123, 37_000           # breakpoint and deletion length (not a multiple of the 4 kb bin)
+    filler = synthetic.random_codes(1, dlen, 106)[0]
+    alt = np.concatenate([ref[:bp], ref[bp + dlen:], filler])   # window start unchanged: downstream bases shift by dlen
+    assert alt.shape == ref.shape
+    wins = [(ref, "chrS", bp, 16_000_000), (alt, "chrS", bp, 16_000_000)]
+    outs, cache = variants.predict_variant_windows(wins, shell)
+    n_blocks = L // 4000 // cache.block_bins
+    upstream = (bp - variants.HALO_BP) // (cache.block_bins * 4000)          # blocks that cannot see the breakpoint
+    assert cache.hits >= 2 * (upstream - 1) and cache.misses <= 2 * (2 * n_blocks - (upstream - 1))
+    print("encoder blocks: %d re-used, %d encoded (of %d)" % (cache.hits, cache.misses, 4 * n_blocks))
+    for (seq, mchr, mpos, wpos), out in zip(wins, outs):
+        single = predict.genomepredict(seq[None], mchr, mpos, wpos, models=[shell])
+        assert out["start_coords"] == single["start_coords"]
+        for a, b in zip(out["predictions"][0], single["predictions"][0]):
+            assert np.array_equal(a, b)
+    # a second call with the same cache encodes nothing new
+    h0, m0 = cache.hits, cache.misses
+    outs2, _ = variants.predict_variant_windows(wins, shell, cache)
+    assert cache.misses == m0 and cache.hits == h0 + 4 * n_blocks
+    assert all(np.array_equal(a, b) for o, o2 in zip(outs, outs2) for a, b in zip(o["predictions"][0], o2["predictions"][0]))
