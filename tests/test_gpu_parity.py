@@ -615,3 +615,45 @@ def test_variant_windows_reuse_encoder_blocks():
     outs2, _ = variants.predict_variant_windows(wins, shell, cache)
     assert cache.misses == m0 and cache.hits == h0 + 4 * n_blocks
     assert all(np.array_equal(a, b) for o, o2 in zip(outs, outs2) for a, b in zip(o["predictions"][0], o2["predictions"][0]))
+
+
+def _nccl_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from orca_b200 import models, parallel
+    g = gold("genomepredict_32mb")
+    shell = models.H1esc(seed=int(g["shell_seed"]), device=dev)
+    seq = torch.from_numpy(synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"])))
+    runner = parallel.ShardedForward(shell, 32_000_000, rank, world, dev)
+    runner.upload(seq)
+    enc_f = runner._encode(False).contiguous()
+    maps = runner.forward(int(g["mpos"]), int(g["wpos"]))
+    if rank == 0:
+        ret["enc"], ret["maps"] = enc_f.cpu(), maps.cpu()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_forward_matches_single_gpu():
+    """World size 2 over NCCL on real GPUs: the all-gathered sharded encoding is BIT-equal to the single-GPU encoding
+    (the chunked encoder is bit-identical to the single pass) and the maps meet the reference fixture."""
+    import torch.multiprocessing as mp
+    from orca_b200 import models, parallel
+    g = gold("genomepredict_32mb")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, 29650 + os.getpid() % 300, ret), nprocs=2, join=True)
+    dev = torch.device("cuda", 0)
+    shell = models.H1esc(seed=int(g["shell_seed"]), device=dev)
+    seq = torch.from_numpy(synthetic.random_sequence(1, 32_000_000, int(g["seq_seed"])))
+    single = parallel.ShardedForward(shell, 32_000_000, 0, 1, dev)
+    single.upload(seq)
+    assert torch.equal(single._encode(False).cpu(), ret["enc"])
+    maps1 = single.forward(int(g["mpos"]), int(g["wpos"])).cpu().numpy()
+    maps2 = ret["maps"].numpy()
+    assert max(relerr(maps2[i], maps1[i]) for i in range(6)) <= 1e-4
+    assert max(relerr(maps2[i], g["predictions"][i]) for i in range(6)) <= TOL
