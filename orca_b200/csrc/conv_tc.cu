@@ -40,8 +40,14 @@ using namespace tcdev;
 
 constexpr int kRows = 136;                       // 128 output rows + 8 halo rows per A slot
 constexpr int kALoOff = 8 * kRows * 16;          // FMT 0: the lo image of a 64-channel K-block follows the hi image
-constexpr int kEpiWarps = 8;                    // two per TMEM lane quarter, each takes every other 32-column group
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 producer, warp 1 MMA issuer, then the epilogue warps
+constexpr int kEpiWarps = 8;                    // epilogue warps per accumulator: two per TMEM lane quarter, each takes every other 32-column group
+// The single-pass fp16 64 -> 64 kernel (stage 1: 32 M positions per strand) issues few MMAs per tile, so its epilogue
+// (residual, ReLU, fused max-pool) is what paces the residual + pool layer: it runs TWO sets of epilogue warps, one per TMEM
+// accumulator (set s drains the tiles that land in accumulator s), i.e. two tiles' epilogues in flight at once (measured:
+// 11.4 -> 9.7 ms per step).  The 96-wide variants spill under the 576-thread register budget (96 registers) and need a
+// smaller pool buffer next to their 166 KB of resident weights: measured slower (8.5 -> 9.1-9.5 ms), so they keep one set.
+__host__ __device__ constexpr int epi_sets(int fmt, int c_out) { return (fmt && c_out == 64) ? 2 : 1; }
+__host__ __device__ constexpr int threads_of(int fmt, int c_out) { return 64 + 32 * kEpiWarps * epi_sets(fmt, c_out); }  // warp 0 producer, warp 1 MMA issuer, then the epilogue warps
 
 struct TcKArgs {
   const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;
@@ -74,7 +80,7 @@ struct TcCfg {
   static constexpr int POOL_CHUNKS = BIG_RESIDENT ? 2 : 4;  // 8-channel chunks per pass of the fused max-pool buffer
   static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
-  static constexpr int POOL_SCRATCH = FMT ? kEpiWarps * POOL_CHUNKS * 512 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
+  static constexpr int POOL_SCRATCH = FMT ? epi_sets(FMT, C_OUT) * kEpiWarps * POOL_CHUNKS * 512 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
   // resident stages are packed back to back (a 32-channel K-block's stages are half size), streamed ones use a ring of
   // full-size slots
   static constexpr int W_BYTES = RESIDENT ? 9 * PARTS * (C_IN / 8) * C_OUT * 16 : NW * STAGE_MAX;
@@ -91,8 +97,9 @@ struct TcCfg {
 // CONCAT: the two products that share A = Ah run as ONE MMA against B = [Bh;Bl] (N = 2*C_OUT, two
 // accumulator column blocks summed in the epilogue) -- 2 MMAs and 2 A-operand reads per K step instead of 3.
 template <int C_IN, int C_OUT, bool CONCAT, int FMT>
-__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a) {
+__global__ void __launch_bounds__(threads_of(FMT, C_OUT), 1) conv1d_tc_kernel(const TcKArgs a) {
   using Cfg = TcCfg<C_IN, C_OUT, FMT>;
+  constexpr int kThreads = threads_of(FMT, C_OUT);
   static_assert(!(FMT && CONCAT), "the single-pass format has nothing to concatenate");
   constexpr int NKB = Cfg::NKB, NW = Cfg::NW, NA = Cfg::NA;
   constexpr int kASlotBytes = Cfg::A_SLOT;
@@ -226,13 +233,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
     // ================= epilogue warps (TMEM lane quarter = warp % 4) =================
     // The epilogue is instruction-latency bound per warp (one warp per scheduler, long dependent chains), so
     // two warps share each lane quarter: warp (q, h) handles the 32-column groups h, h+2, ...
-    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int eset = (warp - 2) / kEpiWarps;  // which accumulator's tiles this warp drains (FMT 1: two sets)
+    const int q = warp & 3, h = ((warp - 2) % kEpiWarps) >> 2;
     if (blockIdx.x == 0 && a.out_hi) {  // zero the pad rows of the output planes (they are the next layer's padding)
       const int et = (warp - 2) * 32 + lane;
       const int planes = a.nb * (C_OUT / 8);
       const int tail0 = a.n_out + 4, ntail = a.npad_out - tail0;
       const int per_plane = 4 + ntail;
-      for (int i = et; i < planes * per_plane; i += 32 * kEpiWarps) {
+      for (int i = et; i < planes * per_plane; i += 32 * kEpiWarps * epi_sets(FMT, C_OUT)) {
         const int p = i / per_plane, j = i - p * per_plane;
         const size_t r = (size_t)p * a.npad_out + (j < 4 ? j : tail0 + (j - 4));
         reinterpret_cast<uint4*>(a.out_hi)[r] = make_uint4(0, 0, 0, 0);
@@ -243,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const TcKArgs a)
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int b = tile / a.tiles_per_sample, t = tile - b * a.tiles_per_sample;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      if (epi_sets(FMT, C_OUT) == 2 && (int)as != eset) { ++acc_it; continue; }  // the other set's tile
       const int l = t * 128 + q * 32 + lane;  // position within the sample
       const bool valid = l < a.n;
       const size_t r_in = (size_t)l + 4;
@@ -380,7 +389,7 @@ int launch_tc_impl(const TcKArgs& a, int sms, cudaStream_t s) {
     configured = true;
   }
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv1d_tc_kernel<C_IN, C_OUT, CONCAT, FMT><<<grid, kThreads, Cfg::SMEM, s>>>(a);
+  conv1d_tc_kernel<C_IN, C_OUT, CONCAT, FMT><<<grid, threads_of(FMT, C_OUT), Cfg::SMEM, s>>>(a);
   ORCA_LAUNCH_OK();
   return ORCA_B200_OK;
 }
