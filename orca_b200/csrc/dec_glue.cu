@@ -53,7 +53,12 @@ __global__ void __launch_bounds__(256) ds_extra_conv_kernel(const float* __restr
   extern __shared__ float sw[];
   for (int i = threadIdx.x; i < n_extra * 9 * 64; i += blockDim.x) sw[i] = __ldg(w + i);
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_iter = (total + stride - 1) / stride;
+  for (long long it = 0; it < n_iter; ++it) {  // uniform trip count: the shuffles below need whole warps
+    const long long i0 = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i0 < total;
+    const long long i = ok ? i0 : total - 8 + (i0 & 7);  // idle threads recompute the last pixel (no store)
     const int ch = (int)(i & 7);
     const long long pix = i >> 3;
     const int x = (int)(pix % S);
@@ -63,17 +68,24 @@ __global__ void __launch_bounds__(256) ds_extra_conv_kernel(const float* __restr
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int e = 0; e < n_extra; ++e) {
       const float* sb = src + b * sB + e * sC;
+      // the 9 (upsampled) source values of this pixel are evaluated ONCE by its 8 threads (lane c: tap c, lane 0 also tap 8)
+      // and exchanged with shuffles, instead of 9 bilinear samples per thread
+      const float mine = extra_src(sb, sH, sW, S, mode, y + ch / 3 - 1, x + ch % 3 - 1);
+      const float last = ch == 0 ? extra_src(sb, sH, sW, S, mode, y + 1, x + 1) : 0.f;
+      const int base = (threadIdx.x & 31) & ~7;
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) {
-        const float v = extra_src(sb, sH, sW, S, mode, y + tp / 3 - 1, x + tp % 3 - 1);
+        const float v = tp < 8 ? __shfl_sync(0xffffffffu, mine, base + tp) : __shfl_sync(0xffffffffu, last, base);
         const float4* wr = reinterpret_cast<const float4*>(sw + (e * 9 + tp) * 64 + ch * 8);
         const float4 w0 = wr[0], w1 = wr[1];
         acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
         acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
       }
     }
-    __nv_bfloat16* p = px_ptr(out, pix, 64) + ch * 8;
-    split_store8(acc, p, p + 64);
+    if (ok) {
+      __nv_bfloat16* p = px_ptr(out, pix, 64) + ch * 8;
+      split_store8(acc, p, p + 64);
+    }
   }
 }
 
