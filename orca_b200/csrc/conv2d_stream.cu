@@ -56,7 +56,7 @@ struct SLayer {
   int c_in, c_out, d, relu;
   int in_c0, in_c1;           // inner (channel) coordinates of the hi and lo input boxes (c_in = 32: one box, in_c1 unused)
   int in_layer, res_layer, war_layer;
-  int NA, NS, drain_before, rot;
+  int NA, NS, drain_before, rot, split;
   int offW, offA, offStg0, offStg1;
   int a_box_bytes, a_slot_bytes, w_bytes, R;
 };
@@ -161,6 +161,7 @@ struct Walk {
   int S, d, q, rem, tpr, cur, end, n_tiles;
   int cur2, end2;  // second piece of a rotated range (single image only)
   int part, nb, img_tiles;
+  bool whole;  // one contiguous piece of the whole tile order (SLayer::split == 0)
   const int2* parts;
   // A CTA owns one contiguous piece of EVERY image (SGeom::parts) and walks them image by image.  With two or more
   // images the tiles of image b in layer l+1 depend on what this and the other CTAs finished half a layer ago (they have
@@ -175,15 +176,28 @@ struct Walk {
     cur = t0 + sft; end = t1;
     cur2 = t0; end2 = t0 + sft;
   }
-  __device__ __forceinline__ void init(const SGeom& g, int d_, int rot) {
+  // split = 1: per-image pieces (used for the first layer of a new dilation, whose dependencies are all-to-all);
+  // split = 0: ONE contiguous piece of the whole order, walked from `rot` (two halo runs per layer instead of 2 x nb)
+  __device__ __forceinline__ void init(const SGeom& g, int d_, int rot, int split) {
     S = g.S; d = d_; tpr = g.tpr; nb = g.nb; img_tiles = g.tpr * g.S;
     q = S / d; rem = S - q * d;
     parts = g.parts + (size_t)blockIdx.x * g.nb;
+    whole = nb > 1 && !split;
+    rot_ = rot;
+    if (whole) {
+      const int t0 = (int)(((long long)blockIdx.x * g.total_tiles) / gridDim.x);
+      const int t1 = (int)(((long long)(blockIdx.x + 1) * g.total_tiles) / gridDim.x);
+      n_tiles = t1 - t0;
+      const int sft = n_tiles > 0 ? rot % n_tiles : 0;
+      cur = t0 + sft; end = t1;
+      cur2 = t0; end2 = t0 + sft;
+      part = nb;  // no further pieces
+      return;
+    }
     n_tiles = 0;
     for (int b = 0; b < nb; ++b) n_tiles += parts[b].y;
     part = 0;
     load_part(rot);
-    rot_ = rot;
   }
   int rot_;
   __device__ __forceinline__ bool next(Seg& s) {
@@ -285,7 +299,7 @@ __device__ __forceinline__ void producer_layer(const SLayer& L, int l, const SGe
   const uint32_t slot_tx = (uint32_t)(L.c_in == 64 ? 2 : 1) * (uint32_t)L.R * 128u;
   const uint32_t stg_tx = (uint32_t)L.c_out * 4u * 128u;  // 128 pixels x (hi + lo) x c_out x 2 B
   Walk w;
-  w.init(g, L.d, L.rot);
+  w.init(g, L.d, L.rot, L.split);
   if (!L.tm_res) stg.skip(L.NS, (uint32_t)w.n_tiles);
   Seg s;
   uint32_t tile_it = 0;
@@ -401,7 +415,7 @@ __device__ __forceinline__ void mma_layer(const SLayer& L, int l, const SGeom& g
   const uint32_t bBase = umma_desc_lo(smem0 + L.offW, 2 * C_OUT * 16);
   const uint32_t dshift = ((uint32_t)L.d * 128u) >> 4;
   Walk w;
-  w.init(g, L.d, L.rot);
+  w.init(g, L.d, L.rot, L.split);
   Seg s;
   while (w.next(s)) {
     const int k_first = run_first(s), k_last = run_last(s);
@@ -463,7 +477,7 @@ __device__ __forceinline__ void epilogue_layer(const SLayer& L, const SGeom& g, 
   const int row = q * 32 + lane;           // pixel within the tile = TMEM lane
   const uint32_t sw = (uint32_t)(row & 7);
   Walk w;
-  w.init(g, L.d, L.rot);
+  w.init(g, L.d, L.rot, L.split);
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
@@ -539,7 +553,7 @@ __device__ __forceinline__ void store_layer(const SLayer& L, int l, const SGeom&
   __syncwarp();
   unsigned int* flags = g.flags + (size_t)l * g.nb * g.S;
   Walk w;
-  w.init(g, L.d, L.rot);
+  w.init(g, L.d, L.rot, L.split);
   Seg s;
   uint32_t tile_it = 0;
   while (w.next(s)) {
@@ -850,6 +864,7 @@ int DecStream::add(const ConvLayer& L, int k_half, int use_bias, const DMap& in,
   impl->stg0_prev = t.offStg0; impl->stg1_prev = t.offStg1; impl->stg_size_prev = stg_size; impl->ns_prev = t.NS;
   // rotation of the tile walk: +2 per consecutive layer with the same dilation (see Walk)
   t.rot = (l > 0 && impl->layers[l - 1].d == t.d) ? impl->layers[l - 1].rot + 2 : 0;
+  t.split = (l == 0 || impl->layers[l - 1].d != t.d) ? 1 : 0;  // per-image pieces where the dependencies are all-to-all
   // ---- dependencies ----
   auto find = [](const std::map<const void*, int>& m, const void* p) { auto it = m.find(p); return it == m.end() ? -1 : it->second; };
   t.in_layer = find(impl->last_writer, in.p);
