@@ -76,8 +76,11 @@ struct TcCfg {
   // layer shared-memory-bandwidth bound (writes of 166 KB + operand reads of ~380 KB per tile through one 128 B/clk port).
   static constexpr bool BIG_RESIDENT = FMT && C_IN == 96 && C_OUT == 96;
   static constexpr int NW = BIG_RESIDENT ? 18 : FMT ? (C_OUT == 128 ? 6 : 9) : (C_OUT == 64 ? 9 : (C_OUT == 96 ? 4 : 3));
-  static constexpr int NA = BIG_RESIDENT ? 3 : FMT ? 4 : (C_OUT == 64 ? 2 : 3);
-  static constexpr int POOL_CHUNKS = BIG_RESIDENT ? 2 : 4;  // 8-channel chunks per pass of the fused max-pool buffer
+  // FMT 2 = FMT 1 with the shared memory re-balanced for the residual + max-pool layer of the resident 96 -> 96 kernel: that
+  // layer is epilogue-bound (ncu: 2.05 ms vs 1.04 ms plain, tensor pipe 31 %), so it gives up one A slot for a pool buffer
+  // that lets all 32 lanes of an epilogue warp reduce in one pass per 32-channel group instead of half of them in two.
+  static constexpr int NA = BIG_RESIDENT ? (FMT == 2 ? 2 : 3) : FMT ? 4 : (C_OUT == 64 ? 2 : 3);
+  static constexpr int POOL_CHUNKS = BIG_RESIDENT ? (FMT == 2 ? 4 : 2) : 4;  // 8-channel chunks per pass of the fused max-pool buffer
   static constexpr int ACC_STRIDE_CAT = C_OUT == 64 ? 128 : 256;  // TMEM columns per accumulator, concat mode
   static constexpr bool RESIDENT = (9 * NKB <= NW);  // all weight stages fit: load once per CTA
   static constexpr int POOL_SCRATCH = FMT ? epi_sets(FMT, C_OUT) * kEpiWarps * POOL_CHUNKS * 512 : 0;  // per-epilogue-warp transpose buffer of the fused max-pool
@@ -406,7 +409,10 @@ int concat_mask() {
 
 template <int C_IN, int C_OUT>
 int launch_tc(const TcKArgs& a, int sms, cudaStream_t s, int fmt) {
-  if (fmt) return launch_tc_impl<C_IN, C_OUT, false, 1>(a, sms, s);
+  if (fmt) {
+    if (C_IN == 96 && C_OUT == 96 && a.pool > 1 && a.out_hi && !a.out_lo) return launch_tc_impl<C_IN, C_OUT, false, (C_IN == 96 && C_OUT == 96) ? 2 : 1>(a, sms, s);
+    return launch_tc_impl<C_IN, C_OUT, false, 1>(a, sms, s);
+  }
   const int bit = C_OUT == 64 ? 1 : (C_OUT == 96 ? 2 : 4);
   if (concat_mask() & bit) return launch_tc_impl<C_IN, C_OUT, true, 0>(a, sms, s);
   return launch_tc_impl<C_IN, C_OUT, false, 0>(a, sms, s);
