@@ -369,7 +369,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_impl(args.kernels)
-    enc16 = _lib.set_encoder_fp16_stages(args.enc_fp16_stages)  # returns the previous (= default) setting, 3
+    enc16 = _lib.set_encoder_fp16_stages(args.enc_fp16_stages)  # returns the previous (= default) setting, 4
     if args.enc_fp16_stages >= 0:
         enc16 = min(args.enc_fp16_stages, 7)
     peaks = load_peaks()

@@ -108,8 +108,8 @@ const char* orca_b200_last_error(void);
  *   ORCA_B200_OPT_ENCODER_FP16_STAGES  Encoder / Net handles: the first n of the Encoder's 7 stages
  *       (orca_modules.py:811-927) run their convolutions as ONE fp16 tensor-core product with fp16 activations; the
  *       remaining stages -- and every other module -- keep fp32-grade arithmetic (operands split into two bf16, three
- *       products).  Default 3: stages 1-3 hold 97 % of the encoder FLOP and their 2^-12 rounding noise is averaged out
- *       by stages 4-7 -- PROVIDED the folded weights are well conditioned: module_create measures
+ *       products).  Default 4: stages 1-4 hold 98.7 % of the encoder FLOP and their 2^-12 rounding noise is averaged out
+ *       by the pooling and convolutions of stages 5-7 -- PROVIDED the folded weights are well conditioned: module_create measures
  *       the spread of the folded weight row norms of those stages (max / median per conv) and the default drops to 0 when
  *       it exceeds 4 (BatchNorm scales spanning orders of magnitude).  0 = three products everywhere; -1 restores the
  *       default; orca_b200_module_get_option returns the effective value.

@@ -14,6 +14,7 @@ ENCODER, ENCODER2, ENCODER2B, ENCODER3, DECODER, DECODER_1M, NET = 1, 2, 3, 4, 5
 UPSAMPLE_NEAREST, UPSAMPLE_BILINEAR = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 OPT_IMPL, OPT_ENCODER_FP16_STAGES = 1, 2
+DEFAULT_FP16_STAGES = 4  # kDefaultFp16Stages in csrc/modules.cu
 STATUS_FP16_RANGE = 1
 
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -115,13 +116,13 @@ def set_impl(impl):
 
 
 def set_encoder_fp16_stages(n):
-    """Default number of leading encoder stages in single-pass fp16 (0..7, -1 = library default 3); returns the
+    """Default number of leading encoder stages in single-pass fp16 (0..7, -1 = library default 4); returns the
     previous effective setting."""
     global options_epoch
     prev = _defaults["encoder_fp16_stages"]
     _defaults["encoder_fp16_stages"] = -1 if n < 0 else min(int(n), 7)
     options_epoch += 1
-    return 3 if prev < 0 else prev
+    return DEFAULT_FP16_STAGES if prev < 0 else prev
 
 
 def apply_options(handle, overrides=None):

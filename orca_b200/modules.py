@@ -209,7 +209,7 @@ class _NativeModule(nn.Module):
 
     def _calibrate_fp16(self, run_small):
         """One-time self-check per set of weights (first forward after they were loaded): run a small window of the real
-        input with stages 1-3 in single-pass fp16 AND with every stage in the fp32-grade format; keep the fast format only
+        input with the default single-pass fp16 stages AND with every stage in the fp32-grade format; keep the fast format only
         if the two agree to CALIBRATION_TOL.  This catches what no static rule does (e.g. heavy-tailed trained weights
         whose few dominant taps stop the fp16 rounding noise from averaging out).  `run_small()` performs the small
         forward under the module's current options and returns one output tensor."""

@@ -70,7 +70,7 @@ def test_encoder_golden(name, impl):
             finally:
                 _lib.set_encoder_fp16_stages(-1)
         print(name, "relerr by fp16 stages", {k: "%.2e" % v for k, v in errs.items()})
-        assert errs[0] <= 5e-5 and errs[3] <= 1e-4 and errs[7] <= TOL
+        assert errs[0] <= 5e-5 and errs[3] <= 1e-4 and errs[4] <= 1e-4 and errs[7] <= TOL
 
 
 def test_encoder_layouts_and_chunks(impl):
@@ -476,7 +476,7 @@ def test_fp16_stages_on_hard_inputs(name):
     if str(g["recipe"]) in ("wide_bn", "heavy_tail"):
         assert fell_back or static_off
         # forced back to single-pass fp16 without the guard, this case misses the bar or trips the guard: the protection matters
-        m.options["encoder_fp16_stages"] = 3
+        m.options["encoder_fp16_stages"] = 4
         bad = m(x, guard=False).cpu().numpy()
         fired = m.fp16_guard_fired()
         print(name, "forced fp16 stages: relerr %.2e, guard fired: %s" % (relerr(bad, g["out"]), fired))

@@ -129,7 +129,7 @@ def test_abi_argument_checks_without_a_gpu():
     # packed encoder input with a zero position stride is rejected before any pointer is looked at
     assert lib.orca_b200_encoder_forward_packed(None, None, 1, 4000, 4000, 0, 0, 0, 4000, None, 0, 1, 0, None, 0, None) == -1
     # kernel selection / precision defaults live on the Python side and reach the library per handle
-    assert _lib.set_encoder_fp16_stages(0) == 3  # previous effective setting: library default, stages 1-3 single-pass
+    assert _lib.set_encoder_fp16_stages(0) == 4  # previous effective setting: library default, stages 1-4 single-pass
     assert _lib.set_encoder_fp16_stages(-1) == 0
     with pytest.raises(ValueError):
         _lib.set_impl("cpu")

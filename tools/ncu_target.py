@@ -1,5 +1,5 @@
 """Single-GPU workload for ncu at the BENCH shapes: one 32 Mb Encoder pass per strand (one chunk, all 7 stages, default
-precision: stages 1-3 single-pass fp16; fp32 one-hot forward strand, packed-base reverse strand read in place), Encoder2 on
+precision: stages 1-4 single-pass fp16; fp32 one-hot forward strand, packed-base reverse strand read in place), Encoder2 on
 both strands, the strand-batched 6-level decoder cascade (+ Decoder_1m) of an H1esc-like shell, and the 256 Mb background
 kernels (assembly of an 8000 x 8000 matrix + one block-mean level).  Usage (under gpurun):
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_target.py
