@@ -53,7 +53,9 @@ class ShardedForward:
         self._uploader, self._staging, self._staging_ev = None, None, None
         self._ready = None
         self._cuts = [self.b0, self.b1]
-        self.pieces = (0.0, 0.125, 0.5, 1.0)  # upload pieces (fractions of this rank's bins) overlapped with the encoder
+        # upload pieces (fractions of this rank's bins) overlapped with the encoder: a small first piece (the encoder starts
+        # after 1/32 of the upload), then growing ones; every extra cut costs one 2 x 112 kb halo recompute
+        self.pieces = (0.0, 0.03125, 0.125, 0.5, 1.0)
         self.concurrent_strands = False  # measured: no gain (the big conv kernels fill the GPU) and 2x workspace
         # how a single GPU runs the two strand cascades: "batch" = the two strands as the two batch elements of ONE
         # chain (every decoder call is one persistent stream kernel at batch 2); "serial" = one strand after the other

@@ -281,3 +281,16 @@ def test_log_normmat_cache_follows_the_source_array():
     sh.normmats[4][10, 10] *= 3.0
     c = predict._log_normmat(sh, 4, cpu)
     assert c is not b and abs(float(c[0, 0, 10, 10] - b[0, 0, 10, 10]) - np.log(3.0)) < 1e-5
+
+
+def test_variant_window_inputs_normalise_to_packed_codes():
+    """orca_b200.variants accepts a window as the reference passes it ((1, L, 4) one-hot), as text / bytes, or as packed
+    codes; all forms must give the same packed bases (the cache keys are hashes of these)."""
+    from orca_b200 import feeder, variants
+    seq = synthetic.random_sequence(1, 8000, 3, 0.02)
+    codes = feeder.from_onehot(seq)[0]
+    text = "".join("ACGTN"[c] for c in codes)
+    for form in (seq, seq[0], codes, codes[None], text, text.encode(), np.frombuffer(text.encode(), dtype=np.uint8)):
+        got = variants._as_codes(form)
+        assert got.dtype == np.uint8 and got.shape == (8000,) and np.array_equal(got, codes)
+    assert variants.HALO_BP == parallel.HALO_BP
